@@ -1,0 +1,56 @@
+"""ctypes binding of libcuembed_b200.so (the C ABI in include/cuembed_b200.h).
+
+The library is the product: if it is missing it is built once with nvcc, and
+if that fails the import raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_LIB = None
+
+# Names and signatures exactly as declared in include/cuembed_b200.h.
+_vp, _ci, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+_szp = ctypes.POINTER(ctypes.c_size_t)
+SIGNATURES = {
+    "cuembed_version": (_ci, []),
+    "cuembed_build_arch": (ctypes.c_char_p, []),
+    "cuembed_error_string": (ctypes.c_char_p, [_ci]),
+    "cuembed_forward": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci,
+                              _ci, _ci, _vp, _ci, _vp]),
+    "cuembed_extract_row_ids_fixed": (_ci, [_ci, _ci, _vp, _ci, _vp]),
+    "cuembed_extract_row_ids_csr": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp]),
+    "cuembed_extract_row_ids_concat": (_ci, [_ci, _vp, _ci, _vp]),
+    "cuembed_transpose": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp,
+                                _vp, _szp, _vp]),
+    "cuembed_compressed_grad_indices": (_ci, [_vp, _ci, _ci, _vp, _vp, _szp, _vp]),
+    "cuembed_backward": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp,
+                               _ci, _vp, _vp, _vp]),
+    "cuembed_backward_ws": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp,
+                                  _vp, _ci, _vp, _vp, _vp, _szp, _vp]),
+    "cuembed_launch_count": (ctypes.c_ulonglong, []),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building if necessary) the CUDA library.  Raises on failure."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib

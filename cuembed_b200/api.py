@@ -1,0 +1,215 @@
+"""Host-side mirror of the cuEmbed operator interface on torch CUDA tensors.
+
+Function names, argument order and meaning follow the reference's host API
+(NVIDIA/cuEmbed, cuembed/include/embedding_lookup.cuh:245-308,423-483 and
+cuembed/include/index_transforms.cuh:45-93,224-250,278-323) so that parity
+tests read like the reference's own tests.  Every function enqueues sm_100a
+kernels from libcuembed_b200.so on the current torch CUDA stream and returns
+without synchronising.  Tensors must live on a CUDA device: there is no CPU
+path (the reference's `Check failed ... abort()` becomes CuEmbedError).
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class CombineMode(enum.IntEnum):
+    """cuembed::CombineMode, cuembed/include/embedding_lookup_types.cuh:29."""
+    kSum = 0
+    kMean = 1
+    kConcat = 2
+
+
+class CuEmbedError(RuntimeError):
+    pass
+
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_IT = {torch.int32: 0, torch.int64: 1}
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        msg = _lib.load().cuembed_error_string(rc).decode()
+        raise CuEmbedError(f"cuembed_b200 error {rc}: {msg}")
+
+
+def _dev(t: Optional[torch.Tensor], name: str) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CuEmbedError(
+            f"{name} must be a CUDA tensor: cuembed_b200 has no CPU fallback")
+    if not t.is_contiguous():
+        raise CuEmbedError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _stream(stream) -> int:
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, torch.cuda.Stream):
+        return stream.cuda_stream
+    return int(stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise CuEmbedError(f"unsupported element dtype {t.dtype}") from None
+
+
+def _it(t: torch.Tensor) -> int:
+    try:
+        return _IT[t.dtype]
+    except KeyError:
+        raise CuEmbedError(f"unsupported index dtype {t.dtype}") from None
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process."""
+    return int(_lib.load().cuembed_launch_count())
+
+
+def EmbeddingForward(params: torch.Tensor, embed_width: int,
+                     indices: torch.Tensor, offsets: Optional[torch.Tensor],
+                     weights: Optional[torch.Tensor], batch_size: int,
+                     num_hots: int, mode: CombineMode, ret: torch.Tensor,
+                     fp16_math: bool = False, stream=None) -> None:
+    """EmbeddingForward<InputT,OutputT,IndexT,OffsetT,fp16_math>
+    (cuembed/include/embedding_lookup.cuh:245-259).  InputT / OutputT / IndexT /
+    OffsetT are taken from the tensor dtypes."""
+    lib = _lib.load()
+    if weights is not None and weights.dtype != params.dtype:
+        raise CuEmbedError("weights must have the element type of params "
+                           "(GetElemT<InputT>, embedding_lookup.cuh:249)")
+    _check(lib.cuembed_forward(
+        _dev(params, "params"), _dt(params), int(embed_width),
+        _dev(indices, "indices"), _it(indices),
+        _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+        _dev(weights, "weights"), int(batch_size), int(num_hots), int(mode),
+        int(bool(fp16_math)), _dev(ret, "ret"), _dt(ret), _stream(stream)))
+
+
+def ExtractRowIdsFromFixed(batch_size: int, num_hots: int,
+                           row_ids: torch.Tensor, stream=None) -> None:
+    """cuembed/include/index_transforms.cuh:45-55."""
+    _check(_lib.load().cuembed_extract_row_ids_fixed(
+        int(batch_size), int(num_hots), _dev(row_ids, "row_ids"), _it(row_ids),
+        _stream(stream)))
+
+
+def ExtractRowIdsFromCSR(offsets: torch.Tensor, batch_size: int,
+                         row_ids: torch.Tensor, stream=None) -> None:
+    """cuembed/include/index_transforms.cuh:66-74."""
+    _check(_lib.load().cuembed_extract_row_ids_csr(
+        _dev(offsets, "offsets"), _it(offsets), int(batch_size),
+        _dev(row_ids, "row_ids"), _it(row_ids), _stream(stream)))
+
+
+def ExtractRowIdsForConcat(nnz: int, row_ids: torch.Tensor, stream=None) -> None:
+    """cuembed/include/index_transforms.cuh:85-93."""
+    _check(_lib.load().cuembed_extract_row_ids_concat(
+        int(nnz), _dev(row_ids, "row_ids"), _it(row_ids), _stream(stream)))
+
+
+def Transpose(rows: torch.Tensor, cols: torch.Tensor,
+              weights: Optional[torch.Tensor], nnz: int,
+              transpose_rows: Optional[torch.Tensor],
+              transpose_cols: Optional[torch.Tensor],
+              transpose_weights: Optional[torch.Tensor],
+              work: Optional[torch.Tensor], stream=None) -> int:
+    """Transpose<IndexT,WeightT> (cuembed/include/index_transforms.cuh:224-234).
+    With work=None this is the workspace query and returns the byte count
+    (the reference writes it to *lwork); otherwise `work` is a uint8 CUDA
+    tensor of at least that size."""
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(0 if work is None else work.numel())
+    ref = cols if cols is not None else transpose_rows
+    wdt = _dt(weights) if weights is not None else 0
+    if work is None:
+        _check(lib.cuembed_transpose(
+            None, None, ctypes.c_void_p(1) if weights is not None else None, wdt,
+            int(nnz), _it(ref), None, None, None, None, ctypes.byref(lwork),
+            _stream(stream)))
+        return int(lwork.value)
+    _check(lib.cuembed_transpose(
+        _dev(rows, "rows"), _dev(cols, "cols"), _dev(weights, "weights"), wdt,
+        int(nnz), _it(cols), _dev(transpose_rows, "transpose_rows"),
+        _dev(transpose_cols, "transpose_cols"),
+        _dev(transpose_weights, "transpose_weights"), _dev(work, "work"),
+        ctypes.byref(lwork), _stream(stream)))
+    return int(lwork.value)
+
+
+def ComputeCompressedGradIndices(indices: torch.Tensor, nnz: int,
+                                 remapped_indices: Optional[torch.Tensor],
+                                 work: Optional[torch.Tensor], stream=None) -> int:
+    """ComputeCompressedGradIndices<IndexT>
+    (cuembed/include/index_transforms.cuh:278-284); work=None is the query."""
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(0 if work is None else work.numel())
+    if work is None:
+        _check(lib.cuembed_compressed_grad_indices(
+            None, _it(indices), int(nnz), None, None, ctypes.byref(lwork),
+            _stream(stream)))
+        return int(lwork.value)
+    _check(lib.cuembed_compressed_grad_indices(
+        _dev(indices, "indices"), _it(indices), int(nnz),
+        _dev(remapped_indices, "remapped_indices"), _dev(work, "work"),
+        ctypes.byref(lwork), _stream(stream)))
+    return int(lwork.value)
+
+
+def EmbeddingBackward(grad_y: torch.Tensor, embed_width: int,
+                      num_grad_embedding_rows: int, nnz: int,
+                      transpose_indices: torch.Tensor,
+                      transpose_sample_ids: torch.Tensor,
+                      transpose_remapped_indices: Optional[torch.Tensor],
+                      transpose_weights: Optional[torch.Tensor],
+                      skip_grad_init: bool, grad_embedding: torch.Tensor,
+                      inverse_mapping: Optional[torch.Tensor],
+                      work: Optional[torch.Tensor] = None, stream=None) -> None:
+    """EmbeddingBackward<GradT,IndexT>
+    (cuembed/include/embedding_lookup.cuh:423-435).  `work` (optional uint8
+    CUDA tensor sized by backward_workspace_bytes) selects the explicit
+    workspace entry point; without it scratch comes from the library's
+    stream-ordered pool."""
+    lib = _lib.load()
+    if transpose_weights is not None and transpose_weights.dtype != grad_y.dtype:
+        raise CuEmbedError("transpose_weights must have the dtype of grad_y")
+    if grad_embedding.dtype != grad_y.dtype:
+        raise CuEmbedError("grad_embedding must have the dtype of grad_y")
+    args = [
+        _dev(grad_y, "grad_y"), _dt(grad_y), int(embed_width),
+        int(num_grad_embedding_rows), int(nnz), _it(transpose_indices),
+        _dev(transpose_indices, "transpose_indices"),
+        _dev(transpose_sample_ids, "transpose_sample_ids"),
+        _dev(transpose_remapped_indices, "transpose_remapped_indices"),
+        _dev(transpose_weights, "transpose_weights"), int(bool(skip_grad_init)),
+        _dev(grad_embedding, "grad_embedding"),
+        _dev(inverse_mapping, "inverse_mapping"),
+    ]
+    if work is None:
+        _check(lib.cuembed_backward(*args, _stream(stream)))
+    else:
+        lwork = ctypes.c_size_t(work.numel())
+        _check(lib.cuembed_backward_ws(*args, _dev(work, "work"),
+                                       ctypes.byref(lwork), _stream(stream)))
+
+
+def backward_workspace_bytes(dtype: torch.dtype, embed_width: int, nnz: int,
+                             index_dtype: torch.dtype = torch.int32) -> int:
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(0)
+    _check(lib.cuembed_backward_ws(
+        None, _DT[dtype], int(embed_width), 0, int(nnz), _IT[index_dtype], None,
+        None, None, None, 1, None, None, None, ctypes.byref(lwork), None))
+    return int(lwork.value)

@@ -1,0 +1,523 @@
+// backward.cu -- deterministic segmented-reduction backward for sm_100a.
+//
+// Replaces EmbeddingBackwardKernel + GradIndexLoader / GradAddresser /
+// GradCombiner + CompactSparseIndicesKernel of the reference
+// (cuembed/include/embedding_lookup_kernels.cuh:175-302,
+//  cuembed/include/embedding_lookup_ops.cuh:499-666), which accumulate in the
+// gradient type and resolve block edges with float atomics (order varies from
+// run to run).  Here:
+//
+//   * the sorted COO is cut into fixed chunks of K nonzeros; a lane group (G
+//     lanes, one V-byte vector of the row per lane) walks its chunk in order,
+//     accumulating weight * grad_y[sample] in fp32 registers, with UNROLL row
+//     loads in flight;
+//   * a run of equal rows that lies inside one chunk is rounded once and
+//     stored directly; a run that crosses chunk edges leaves a head / tail
+//     partial in shared memory, and the CTA stitches its chunks in chunk order;
+//   * runs that cross CTA edges leave one head and one tail partial per CTA in
+//     a small fp32 scratch; a second kernel adds them in CTA order.
+//   Every sum therefore has a fixed association order: results are identical
+//   from run to run, with one rounding to the gradient type per element.
+//   * inverse_mapping (compressed gradients) is written where each run ends,
+//     so the separate compaction kernel of the reference disappears.
+//   * 64-bit row offsets throughout (the reference's `int` arithmetic,
+//     embedding_lookup_ops.cuh:610-618, overflows at rows*width >= 2^31).
+//
+// L2/HBM-bound gather + stream-out: no tensor cores.
+#include "common.cuh"
+#include "launch.h"
+
+namespace cuembed_b200 {
+
+struct BwdArgs {
+  const void* grad_y;
+  const void* keys;  // remapped indices if compressed, else table indices
+  const void* tidx;  // table indices (for inverse_mapping) or nullptr
+  const void* sids;
+  const void* weights;
+  void* grad;
+  void* inverse_mapping;
+  float* scratch;       // [num_ctas][2][width]
+  int* meta;            // [num_ctas][2] : head kind, has tail
+  long long* meta_row;  // [num_ctas][2] : head row, tail row
+  int64_t row_bytes;
+  int width;
+  int nnz;
+  int nvec;
+  int lanes;
+  int log2_lanes;
+  int rounds;  // rounds of G nonzeros per lane group (K = G * rounds)
+  int cta_nz;  // nonzeros per CTA = 256 * rounds
+  int num_ctas;
+};
+
+constexpr int kHeadNone = 0;
+constexpr int kHeadEnds = 1;     // first run of the chunk started earlier, ends here
+constexpr int kHeadThrough = 2;  // whole chunk lies inside one earlier run
+
+template <typename IdxT>
+__device__ __forceinline__ uint64_t GradRowOffset(IdxT row, uint32_t row_bytes) {
+  if constexpr (sizeof(IdxT) == 4) {
+    return static_cast<uint64_t>(static_cast<uint32_t>(row)) * row_bytes;
+  } else {
+    return static_cast<uint64_t>(row) * row_bytes;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void StoreOneAs(T* p, float v);
+template <>
+__device__ __forceinline__ void StoreOneAs<float>(float* p, float v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void StoreOneAs<__half>(__half* p, float v) {
+  *p = __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ void StoreOneAs<__nv_bfloat16>(__nv_bfloat16* p,
+                                                          float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+template <typename T, int V, typename IdxT, bool WEIGHTED, int UNROLL>
+__global__ void __launch_bounds__(kCtaThreads, 3)
+    BwdSegReduceKernel(const BwdArgs a) {
+  using VecT = typename VecBits<V>::type;
+  constexpr int NW = V / 4;
+  constexpr int NE = NW * Elem<T>::kPerWord;
+  constexpr unsigned kFull = 0xffffffffu;
+
+  __shared__ float s_part[2][kCtaThreads * NE];
+  __shared__ long long s_row[2][kCtaThreads];
+  __shared__ int s_kind[kCtaThreads];
+  __shared__ int s_tail[kCtaThreads];
+
+  const int tid = threadIdx.x;
+  const int G = a.lanes;
+  const int lane_g = tid & (G - 1);
+  const int g = tid >> a.log2_lanes;
+  const int groups_per_cta = kCtaThreads >> a.log2_lanes;
+  const int gl0 = (tid & 31) & ~(G - 1);  // first lane of this group in the warp
+  // One bit per lane group of the warp (bit k*G), to test "does any group end
+  // a run at position j" with a warp-uniform branch.
+  unsigned patt = 0;
+  for (int k = 0; k < 32; k += G) patt |= 1u << k;
+
+  const IdxT* __restrict__ keys = static_cast<const IdxT*>(a.keys);
+  const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
+  const T* __restrict__ weights = static_cast<const T*>(a.weights);
+  const IdxT* __restrict__ tidx = static_cast<const IdxT*>(a.tidx);
+  const uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+
+  const int K = G * a.rounds;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * a.cta_nz +
+                     static_cast<int64_t>(g) * K;
+  int n_g = 0;
+  if (c0 < a.nnz)
+    n_g = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
+
+  const int v = blockIdx.y * G + lane_g;
+  const bool active = v < a.nvec;
+  const char* __restrict__ gy = static_cast<const char*>(a.grad_y) +
+                                static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+
+  // Does the first run of this chunk continue a run of the previous chunk?
+  bool cont = false;
+  if (n_g > 0 && c0 > 0) cont = __ldg(keys + c0 - 1) == __ldg(keys + c0);
+  bool in_first = true;
+  bool open = false;
+  int head_kind = kHeadNone;
+  IdxT head_row = 0;
+
+  float acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+
+#pragma unroll 1
+  for (int r = 0; r < a.rounds; ++r) {
+    const int cnt = max(0, min(G, n_g - r * G));
+    const int64_t i = c0 + r * G + lane_g;
+    IdxT key = 0, sid = 0;
+    T w = T();
+    bool end = false;
+    if (lane_g < cnt) {
+      key = __ldg(keys + i);
+      sid = __ldg(sids + i);
+      if constexpr (WEIGHTED) w = __ldg(weights + i);
+      end = (i == a.nnz - 1) || (__ldg(keys + i + 1) != key);
+    }
+    const unsigned endsw = __ballot_sync(kFull, end);
+    const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(kFull, cnt);
+
+#pragma unroll 1
+    for (int jb = 0; jb < cnt_max; jb += UNROLL) {
+      VecT vals[UNROLL];
+      T wv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int src = (jb + u) & (G - 1);
+        IdxT s;
+        if constexpr (sizeof(IdxT) == 8)
+          s = static_cast<IdxT>(
+              __shfl_sync(kFull, static_cast<long long>(sid), src, G));
+        else
+          s = __shfl_sync(kFull, sid, src, G);
+        if constexpr (WEIGHTED) {
+          if constexpr (sizeof(T) == 4) {
+            wv[u] = __shfl_sync(kFull, w, src, G);
+          } else {
+            unsigned short b = *reinterpret_cast<unsigned short*>(&w);
+            unsigned rb = __shfl_sync(kFull, static_cast<unsigned>(b), src, G);
+            unsigned short rs = static_cast<unsigned short>(rb);
+            wv[u] = *reinterpret_cast<T*>(&rs);
+          }
+        }
+        // Positions past the end of the chunk carry sample id 0: a valid,
+        // harmless load that is never accumulated.
+        vals[u] = LdgVec<V>(gy + GradRowOffset<IdxT>(s, row_bytes));
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int j = jb + u;
+        if (j < cnt) {
+          uint32_t wd[NW];
+          Unpack32(vals[u], wd);
+#pragma unroll
+          for (int q = 0; q < NW; ++q) {
+            float f[Elem<T>::kPerWord];
+            Elem<T>::WordToFloat(wd[q], f);
+#pragma unroll
+            for (int k = 0; k < Elem<T>::kPerWord; ++k) {
+              float& x = acc[q * Elem<T>::kPerWord + k];
+              if constexpr (WEIGHTED)
+                x = __fadd_rn(x, __fmul_rn(f[k], Elem<T>::ToFloat(wv[u])));
+              else
+                x = __fadd_rn(x, f[k]);
+            }
+          }
+          open = true;
+        }
+        // Warp-uniform test: does any lane group of this warp end a run at j?
+        if (j < G && (endsw & (patt << j)) != 0u) {
+          IdxT krow;
+          if constexpr (sizeof(IdxT) == 8)
+            krow = static_cast<IdxT>(
+                __shfl_sync(kFull, static_cast<long long>(key), j, G));
+          else
+            krow = __shfl_sync(kFull, key, j, G);
+          if (((endsw >> (gl0 + j)) & 1u) != 0u) {
+            if (in_first && cont) {
+              // Run began in an earlier chunk: partial, stitched below.
+#pragma unroll
+              for (int e = 0; e < NE; ++e) s_part[0][tid * NE + e] = acc[e];
+              head_kind = kHeadEnds;
+              head_row = krow;
+            } else if (active) {
+              StoreFloatsAs<NE>(static_cast<char*>(a.grad) +
+                                    GradRowOffset<IdxT>(krow, row_bytes),
+                                static_cast<int64_t>(v) * NE, Elem<T>::kCode,
+                                acc);
+            }
+            if (a.inverse_mapping != nullptr && lane_g == 0 &&
+                blockIdx.y == 0) {
+              static_cast<IdxT*>(a.inverse_mapping)[krow] =
+                  __ldg(tidx + c0 + r * G + j);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+            in_first = false;
+            open = false;
+          }
+        }
+      }
+    }
+  }
+
+  // Leftover: the last run of the chunk continues into the next chunk.
+  int has_tail = 0;
+  IdxT tail_row = 0;
+  if (open) {
+    if (in_first && cont) {
+      head_kind = kHeadThrough;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) s_part[0][tid * NE + e] = acc[e];
+    } else {
+      has_tail = 1;
+      tail_row = __ldg(keys + c0 + n_g - 1);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) s_part[1][tid * NE + e] = acc[e];
+    }
+  }
+  if (lane_g == 0) {
+    s_kind[g] = head_kind;
+    s_tail[g] = has_tail;
+    s_row[0][g] = static_cast<long long>(head_row);
+    s_row[1][g] = static_cast<long long>(tail_row);
+  }
+  __syncthreads();
+
+  // ---- stitch the chunks of this CTA in chunk order (one thread per column
+  //      of the row tile); what crosses the CTA edge goes to the scratch.
+  const int tile_cols = G * NE;
+  if (tid < tile_cols) {
+    const int col = blockIdx.y * tile_cols + tid;
+    const bool col_ok = col < a.width;
+    float* scratch_head =
+        a.scratch + (static_cast<size_t>(blockIdx.x) * 2 + 0) * a.width;
+    float* scratch_tail =
+        a.scratch + (static_cast<size_t>(blockIdx.x) * 2 + 1) * a.width;
+    T* grad = static_cast<T*>(a.grad);
+    float carry = 0.f;
+    bool carry_valid = false, origin_before = false;
+    long long carry_row = 0;
+    int cta_head_kind = kHeadNone, cta_has_tail = 0;
+    long long cta_head_row = 0, cta_tail_row = 0;
+    for (int q = 0; q < groups_per_cta; ++q) {
+      const int hk = s_kind[q];
+      if (hk == kHeadThrough) {
+        if (!carry_valid) {
+          carry = 0.f;
+          carry_valid = true;
+          origin_before = true;
+        }
+        carry = __fadd_rn(carry, s_part[0][q * tile_cols + tid]);
+      } else {
+        if (hk == kHeadEnds) {
+          if (!carry_valid) {
+            carry = 0.f;
+            origin_before = true;
+          }
+          const float total = __fadd_rn(carry, s_part[0][q * tile_cols + tid]);
+          if (origin_before) {
+            if (col_ok) scratch_head[col] = total;
+            cta_head_kind = kHeadEnds;
+            cta_head_row = s_row[0][q];
+          } else if (col_ok) {
+            StoreOneAs<T>(grad + s_row[0][q] * a.width + col, total);
+          }
+          carry_valid = false;
+          origin_before = false;
+        }
+        if (s_tail[q] != 0) {
+          carry = s_part[1][q * tile_cols + tid];
+          carry_valid = true;
+          origin_before = false;
+          carry_row = s_row[1][q];
+        }
+      }
+    }
+    if (carry_valid) {
+      if (origin_before) {
+        cta_head_kind = kHeadThrough;
+        if (col_ok) scratch_head[col] = carry;
+      } else {
+        cta_has_tail = 1;
+        cta_tail_row = carry_row;
+        if (col_ok) scratch_tail[col] = carry;
+      }
+    }
+    if (tid == 0) {
+      a.meta[blockIdx.x * 2 + 0] = cta_head_kind;
+      a.meta[blockIdx.x * 2 + 1] = cta_has_tail;
+      a.meta_row[blockIdx.x * 2 + 0] = cta_head_row;
+      a.meta_row[blockIdx.x * 2 + 1] = cta_tail_row;
+    }
+  }
+}
+
+// Adds, in CTA order, the partials of every run that crosses CTA edges:
+// tail of the CTA where the run starts + heads of the following CTAs.
+template <typename T>
+__global__ void __launch_bounds__(kCtaThreads)
+    BwdFixupKernel(const BwdArgs a) {
+  const int cta = blockIdx.x;
+  if (a.meta[cta * 2 + 1] == 0) return;
+  const int col = blockIdx.y * kCtaThreads + threadIdx.x;
+  if (col >= a.width) return;
+  float acc = a.scratch[(static_cast<size_t>(cta) * 2 + 1) * a.width + col];
+  for (int c = cta + 1; c < a.num_ctas; ++c) {
+    const int kind = a.meta[c * 2 + 0];
+    if (kind == kHeadNone) break;
+    acc = __fadd_rn(acc,
+                    a.scratch[(static_cast<size_t>(c) * 2 + 0) * a.width + col]);
+    if (kind == kHeadEnds) break;
+  }
+  const long long row = a.meta_row[cta * 2 + 1];
+  StoreOneAs<T>(static_cast<T*>(a.grad) + row * a.width + col, acc);
+}
+
+namespace {
+
+int Log2i(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+struct BwdLayout {
+  int rounds;
+  int cta_nz;
+  int num_ctas;
+  size_t scratch_off, meta_off, row_off, total;
+};
+
+BwdLayout MakeBwdLayout(int nnz, int embed_width) {
+  BwdLayout L;
+  static const int rounds_env = EnvInt("CUEMBED_BWD_ROUNDS", 0);
+  int rounds = rounds_env;
+  if (rounds <= 0) {
+    // Nonzeros per CTA: as large as possible (short cross-CTA chains, little
+    // scratch) while leaving >= ~8 CTAs per SM.
+    const int64_t target = static_cast<int64_t>(nnz) /
+                           (static_cast<int64_t>(GetDeviceInfo().sm_count) * 8);
+    rounds = 1;
+    while (rounds < 8 && static_cast<int64_t>(rounds) * 2 * kCtaThreads <= target)
+      rounds *= 2;
+  }
+  L.rounds = rounds;
+  L.cta_nz = rounds * kCtaThreads;
+  L.num_ctas = nnz > 0 ? (nnz + L.cta_nz - 1) / L.cta_nz : 0;
+  size_t off = 0;
+  L.scratch_off = off;
+  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * embed_width * sizeof(float),
+                 256);
+  L.meta_off = off;
+  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * sizeof(int), 256);
+  L.row_off = off;
+  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * sizeof(long long), 256);
+  L.total = off > 0 ? off : 256;
+  return L;
+}
+
+template <typename T, int V, typename IdxT, bool WEIGHTED>
+void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
+  static const int unroll = EnvInt("CUEMBED_BWD_UNROLL", 8);
+  dim3 grid(a.num_ctas, col_tiles);
+  if (unroll == 4)
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4>
+        <<<grid, kCtaThreads, 0, stream>>>(a);
+  else
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8>
+        <<<grid, kCtaThreads, 0, stream>>>(a);
+  dim3 fgrid(a.num_ctas, (a.width + kCtaThreads - 1) / kCtaThreads);
+  BwdFixupKernel<T><<<fgrid, kCtaThreads, 0, stream>>>(a);
+  CountLaunch(2);
+}
+
+template <typename T, int V>
+void LaunchSegReduceIdx(const BwdArgs& a, int idx_type, bool weighted,
+                        int col_tiles, cudaStream_t stream) {
+  if (idx_type == CUEMBED_I64) {
+    if (weighted)
+      LaunchSegReduce<T, V, int64_t, true>(a, col_tiles, stream);
+    else
+      LaunchSegReduce<T, V, int64_t, false>(a, col_tiles, stream);
+  } else {
+    if (weighted)
+      LaunchSegReduce<T, V, int32_t, true>(a, col_tiles, stream);
+    else
+      LaunchSegReduce<T, V, int32_t, false>(a, col_tiles, stream);
+  }
+}
+
+template <typename T>
+void LaunchSegReduceVec(const BwdArgs& a, int vec_bytes, int idx_type,
+                        bool weighted, int col_tiles, cudaStream_t stream) {
+  if (vec_bytes == 16)
+    LaunchSegReduceIdx<T, 16>(a, idx_type, weighted, col_tiles, stream);
+  else if (vec_bytes == 8)
+    LaunchSegReduceIdx<T, 8>(a, idx_type, weighted, col_tiles, stream);
+  else
+    LaunchSegReduceIdx<T, 4>(a, idx_type, weighted, col_tiles, stream);
+}
+
+}  // namespace
+
+int LaunchBackward(const void* grad_y, int dtype, int embed_width,
+                   int num_grad_embedding_rows, int nnz, int idx_type,
+                   const void* transpose_indices,
+                   const void* transpose_sample_ids,
+                   const void* transpose_remapped_indices,
+                   const void* transpose_weights, int skip_grad_init,
+                   void* grad_embedding, void* inverse_mapping, char* work,
+                   size_t* lwork, cudaStream_t stream) {
+  if (lwork == nullptr || nnz < 0 || embed_width <= 0 ||
+      num_grad_embedding_rows < 0)
+    return CUEMBED_ERR_ARGUMENT;
+  if (dtype < 0 || dtype > 2 || idx_type < 0 || idx_type > 1)
+    return CUEMBED_ERR_DTYPE;
+  const int64_t row_bytes = static_cast<int64_t>(embed_width) * ElemSize(dtype);
+  if (row_bytes % 4 != 0) return CUEMBED_ERR_ROW_BYTES;
+  const BwdLayout L = MakeBwdLayout(nnz, embed_width);
+  if (work == nullptr) {
+    *lwork = L.total;
+    return CUEMBED_OK;
+  }
+  if (*lwork < L.total) return CUEMBED_ERR_WORKSPACE;
+  if (grad_embedding == nullptr && (nnz > 0 || !skip_grad_init))
+    return CUEMBED_ERR_ARGUMENT;
+
+  // Zero-fill unless told otherwise (cuembed/include/embedding_lookup.cuh:455-461).
+  if (!skip_grad_init && num_grad_embedding_rows > 0) {
+    if (cudaMemsetAsync(grad_embedding, 0,
+                        static_cast<size_t>(num_grad_embedding_rows) *
+                            static_cast<size_t>(row_bytes),
+                        stream) != cudaSuccess)
+      return CUEMBED_ERR_CUDA;
+  }
+  if (nnz == 0) return CUEMBED_OK;
+  if (grad_y == nullptr || transpose_indices == nullptr ||
+      transpose_sample_ids == nullptr)
+    return CUEMBED_ERR_ARGUMENT;
+  if (transpose_remapped_indices != nullptr && inverse_mapping == nullptr)
+    return CUEMBED_ERR_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(work) & 15) != 0)
+    return CUEMBED_ERR_ARGUMENT;
+
+  RowShape shape;
+  MakeRowShape(embed_width, dtype, &shape);
+  // Vector width limited by the actual pointer alignment.
+  int v = shape.vec_bytes;
+  const uint64_t bits = reinterpret_cast<uint64_t>(grad_y) |
+                        reinterpret_cast<uint64_t>(grad_embedding) |
+                        static_cast<uint64_t>(row_bytes);
+  while (v > 4 && (bits % v) != 0) v /= 2;
+  if ((bits % v) != 0) return CUEMBED_ERR_ARGUMENT;
+
+  BwdArgs a;
+  a.grad_y = grad_y;
+  a.keys = transpose_remapped_indices != nullptr ? transpose_remapped_indices
+                                                 : transpose_indices;
+  a.tidx = transpose_remapped_indices != nullptr ? transpose_indices : nullptr;
+  a.sids = transpose_sample_ids;
+  a.weights = transpose_weights;
+  a.grad = grad_embedding;
+  a.inverse_mapping =
+      transpose_remapped_indices != nullptr ? inverse_mapping : nullptr;
+  a.scratch = reinterpret_cast<float*>(work + L.scratch_off);
+  a.meta = reinterpret_cast<int*>(work + L.meta_off);
+  a.meta_row = reinterpret_cast<long long*>(work + L.row_off);
+  a.row_bytes = row_bytes;
+  a.width = embed_width;
+  a.nnz = nnz;
+  a.nvec = static_cast<int>(row_bytes / v);
+  a.lanes = Pow2Ceil(a.nvec) < 32 ? Pow2Ceil(a.nvec) : 32;
+  a.log2_lanes = Log2i(a.lanes);
+  a.rounds = L.rounds;
+  a.cta_nz = L.cta_nz;
+  a.num_ctas = L.num_ctas;
+  const int col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
+  const bool weighted = transpose_weights != nullptr;
+
+  if (dtype == CUEMBED_F32)
+    LaunchSegReduceVec<float>(a, v, idx_type, weighted, col_tiles, stream);
+  else if (dtype == CUEMBED_F16)
+    LaunchSegReduceVec<__half>(a, v, idx_type, weighted, col_tiles, stream);
+  else
+    LaunchSegReduceVec<__nv_bfloat16>(a, v, idx_type, weighted, col_tiles,
+                                      stream);
+  return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+}
+
+}  // namespace cuembed_b200

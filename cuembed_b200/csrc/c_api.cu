@@ -1,0 +1,176 @@
+// c_api.cu -- the extern "C" boundary declared in include/cuembed_b200.h.
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace cuembed_b200 {
+
+static std::atomic<unsigned long long> g_launches{0};
+
+void CountLaunch(int n) { g_launches.fetch_add(static_cast<unsigned>(n)); }
+
+int EnvInt(const char* name, int default_value) {
+  const char* v = std::getenv(name);
+  if (v == nullptr || *v == '\0') return default_value;
+  return std::atoi(v);
+}
+
+}  // namespace cuembed_b200
+
+using namespace cuembed_b200;  // NOLINT
+
+extern "C" {
+
+int cuembed_version(void) { return 100; }
+
+const char* cuembed_build_arch(void) { return "sm_100a"; }
+
+const char* cuembed_error_string(int code) {
+  switch (code) {
+    case CUEMBED_OK:
+      return "ok";
+    case CUEMBED_ERR_WEIGHTED_CONCAT:
+      return "Check failed: weights == nullptr || mode != CombineMode::kConcat";
+    case CUEMBED_ERR_CSR_XOR_FIXED:
+      return "Check failed: (offsets != nullptr && num_hots == 0) || "
+             "(offsets == nullptr && num_hots > 0)";
+    case CUEMBED_ERR_CSR_CONCAT:
+      return "Check failed: offsets == nullptr || mode != CombineMode::kConcat";
+    case CUEMBED_ERR_ROW_BYTES:
+      return "Check failed: bytes_per_row % 4 == 0";
+    case CUEMBED_ERR_DTYPE:
+      return "unsupported dtype / index type / mode combination";
+    case CUEMBED_ERR_WORKSPACE:
+      return "Check failed: *lwork >= required_workspace";
+    case CUEMBED_ERR_ARGUMENT:
+      return "null pointer, negative size or misaligned buffer";
+    case CUEMBED_ERR_CUDA:
+      return "a CUDA runtime call or kernel launch failed";
+    case CUEMBED_ERR_NNZ_LIMIT:
+      return "nnz must be < 2^30 for transpose";
+    default:
+      return "unknown error";
+  }
+}
+
+int cuembed_forward(const void* params, int in_dtype, int embed_width,
+                    const void* indices, int idx_type, const void* offsets,
+                    int off_type, const void* weights, int batch_size,
+                    int num_hots, int mode, int fp16_math, void* ret,
+                    int out_dtype, cuembed_stream_t stream) {
+  return LaunchForward(params, in_dtype, embed_width, indices, idx_type,
+                       offsets, off_type, weights, batch_size, num_hots, mode,
+                       fp16_math, ret, out_dtype,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
+                                  int idx_type, cuembed_stream_t stream) {
+  return LaunchExtractRowIdsFixed(batch_size, num_hots, row_ids, idx_type,
+                                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_extract_row_ids_csr(const void* offsets, int off_type,
+                                int batch_size, void* row_ids, int idx_type,
+                                cuembed_stream_t stream) {
+  return LaunchExtractRowIdsCsr(offsets, off_type, batch_size, row_ids,
+                                idx_type,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_extract_row_ids_concat(int nnz, void* row_ids, int idx_type,
+                                   cuembed_stream_t stream) {
+  return LaunchExtractRowIdsConcat(nnz, row_ids, idx_type,
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_transpose(const void* rows, const void* cols, const void* weights,
+                      int weight_dtype, int nnz, int idx_type,
+                      void* transpose_rows, void* transpose_cols,
+                      void* transpose_weights, char* work, size_t* lwork,
+                      cuembed_stream_t stream) {
+  return LaunchTranspose(rows, cols, weights, weight_dtype, nnz, idx_type,
+                         transpose_rows, transpose_cols, transpose_weights,
+                         work, lwork, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_compressed_grad_indices(const void* indices, int idx_type, int nnz,
+                                    void* remapped_indices, char* work,
+                                    size_t* lwork, cuembed_stream_t stream) {
+  return LaunchCompressedGradIndices(indices, idx_type, nnz, remapped_indices,
+                                     work, lwork,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
+                        int num_grad_embedding_rows, int nnz, int idx_type,
+                        const void* transpose_indices,
+                        const void* transpose_sample_ids,
+                        const void* transpose_remapped_indices,
+                        const void* transpose_weights, int skip_grad_init,
+                        void* grad_embedding, void* inverse_mapping,
+                        char* work, size_t* lwork, cuembed_stream_t stream) {
+  return LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows,
+                        nnz, idx_type, transpose_indices, transpose_sample_ids,
+                        transpose_remapped_indices, transpose_weights,
+                        skip_grad_init, grad_embedding, inverse_mapping, work,
+                        lwork, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Scratch for the drop-in signature (no workspace argument): a library-owned
+// stream-ordered pool per device that keeps its memory between calls, so the
+// steady state costs no driver allocation.  cudaMallocFromPoolAsync /
+// cudaFreeAsync are stream-ordered and CUDA-graph capturable.
+int cuembed_backward(const void* grad_y, int dtype, int embed_width,
+                     int num_grad_embedding_rows, int nnz, int idx_type,
+                     const void* transpose_indices,
+                     const void* transpose_sample_ids,
+                     const void* transpose_remapped_indices,
+                     const void* transpose_weights, int skip_grad_init,
+                     void* grad_embedding, void* inverse_mapping,
+                     cuembed_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  size_t lwork = 0;
+  int rc = LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows,
+                          nnz, idx_type, transpose_indices,
+                          transpose_sample_ids, transpose_remapped_indices,
+                          transpose_weights, skip_grad_init, grad_embedding,
+                          inverse_mapping, nullptr, &lwork, stream);
+  if (rc != CUEMBED_OK) return rc;
+  if (nnz == 0 && skip_grad_init) return CUEMBED_OK;
+
+  static cudaMemPool_t pools[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return CUEMBED_ERR_CUDA;
+  if (pools[dev] == nullptr) {
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) return CUEMBED_ERR_CUDA;
+    unsigned long long threshold = ~0ull;  // never trim: reuse across calls
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    pools[dev] = pool;
+  }
+  void* work = nullptr;
+  if (cudaMallocFromPoolAsync(&work, lwork, pools[dev], stream) != cudaSuccess)
+    return CUEMBED_ERR_CUDA;
+  rc = LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows, nnz,
+                      idx_type, transpose_indices, transpose_sample_ids,
+                      transpose_remapped_indices, transpose_weights,
+                      skip_grad_init, grad_embedding, inverse_mapping,
+                      static_cast<char*>(work), &lwork, stream);
+  cudaFreeAsync(work, stream);
+  return rc;
+}
+
+unsigned long long cuembed_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

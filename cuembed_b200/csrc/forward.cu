@@ -1,0 +1,251 @@
+// forward.cu -- gather-pool forward kernels (sum / mean / concat) for sm_100a.
+//
+// Replaces the reference's EmbeddingLookUpKernel + IndexLoader / Addresser /
+// Combiner policy classes (cuembed/include/embedding_lookup_kernels.cuh:34-170,
+// cuembed/include/embedding_lookup_ops.cuh:72-495) with one design:
+//
+//   * a lane GROUP (G = 8..32 lanes, chosen from the row width) owns one bag at
+//     a time; each lane owns one V-byte vector (V = 16 where the row allows) of
+//     the row and accumulates it in registers, sequentially in bag order -- the
+//     same order as the reference CPU loop, so fp32 results are bit-identical;
+//   * indices (and weights) are loaded one coalesced round of G at a time,
+//     two rounds ahead of use, and broadcast with group-scoped shuffles: no
+//     shared memory, no CTA-wide barrier, CSR bags do not serialise an index
+//     load in front of every row load;
+//   * UNROLL row loads (16 B each, read-only path) are issued back to back
+//     before any is consumed: UNROLL x 512 B in flight per warp;
+//   * a persistent grid (SM count x resident CTAs) walks the bags.
+//
+// HBM/L2-bound byte work: no tensor cores (nothing here is a contraction).
+#include "common.cuh"
+#include "forward_kernels.cuh"
+#include "launch.h"
+
+namespace cuembed_b200 {
+
+namespace {
+
+int Log2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// Persistent grid: SM count x resident CTAs of this kernel, capped by the
+// amount of work.  `occ_cache` is a per-instantiation static of the caller.
+int PersistentGrid(const void* kernel, int* occ_cache, int64_t work_ctas) {
+  if (*occ_cache == 0) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kCtaThreads, 0);
+    *occ_cache = n > 0 ? n : 1;
+  }
+  const int64_t cap =
+      static_cast<int64_t>(GetDeviceInfo().sm_count) * (*occ_cache);
+  int64_t g = work_ctas < cap ? work_ctas : cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP>
+void LaunchPool(const FwdArgs& a, cudaStream_t stream) {
+  static const int unroll = EnvInt("CUEMBED_FWD_UNROLL", 8);
+  const int groups_per_cta = kCtaThreads / a.lanes;
+  const int64_t work_ctas = (a.batch + groups_per_cta - 1) / groups_per_cta;
+  static int occ4 = 0, occ8 = 0, occ16 = 0;
+  if (unroll == 4) {
+    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 4>;
+    const int grid =
+        PersistentGrid(reinterpret_cast<const void*>(k), &occ4, work_ctas);
+    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
+  } else if (unroll == 16 && V == 16) {
+    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, (V == 16 ? 16 : 8)>;
+    const int grid =
+        PersistentGrid(reinterpret_cast<const void*>(k), &occ16, work_ctas);
+    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
+  } else {
+    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 8>;
+    const int grid =
+        PersistentGrid(reinterpret_cast<const void*>(k), &occ8, work_ctas);
+    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
+  }
+  CountLaunch();
+}
+
+template <typename T, int V, typename IdxT>
+void LaunchPoolFlags(const FwdArgs& a, bool weighted, bool lowp,
+                     cudaStream_t stream) {
+  if constexpr (sizeof(T) == 4) {
+    // fp16_math is a no-op for fp32 tables
+    // (cuembed/include/embedding_lookup_types.cuh:497-551).
+    if (weighted)
+      LaunchPool<T, V, IdxT, true, false>(a, stream);
+    else
+      LaunchPool<T, V, IdxT, false, false>(a, stream);
+  } else {
+    if (weighted && lowp)
+      LaunchPool<T, V, IdxT, true, true>(a, stream);
+    else if (weighted)
+      LaunchPool<T, V, IdxT, true, false>(a, stream);
+    else if (lowp)
+      LaunchPool<T, V, IdxT, false, true>(a, stream);
+    else
+      LaunchPool<T, V, IdxT, false, false>(a, stream);
+  }
+}
+
+template <typename T, typename IdxT>
+void LaunchPoolVec(const FwdArgs& a, int vec_bytes, bool weighted, bool lowp,
+                   cudaStream_t stream) {
+  if (vec_bytes == 16)
+    LaunchPoolFlags<T, 16, IdxT>(a, weighted, lowp, stream);
+  else if (vec_bytes == 8)
+    LaunchPoolFlags<T, 8, IdxT>(a, weighted, lowp, stream);
+  else
+    LaunchPoolFlags<T, 4, IdxT>(a, weighted, lowp, stream);
+}
+
+template <typename T>
+void LaunchPoolIdx(const FwdArgs& a, int idx_type, int vec_bytes,
+                   bool weighted, bool lowp, cudaStream_t stream) {
+  if (idx_type == CUEMBED_I64)
+    LaunchPoolVec<T, int64_t>(a, vec_bytes, weighted, lowp, stream);
+  else
+    LaunchPoolVec<T, int32_t>(a, vec_bytes, weighted, lowp, stream);
+}
+
+template <int V, typename IdxT>
+void LaunchConcat(const ConcatArgs& a, cudaStream_t stream) {
+  auto k = FwdConcatKernel<V, IdxT>;
+  const int groups_per_cta = kCtaThreads / a.lanes;
+  const int64_t work_ctas =
+      (a.nnz + static_cast<int64_t>(groups_per_cta) * 4 - 1) /
+      (static_cast<int64_t>(groups_per_cta) * 4);
+  static int occ = 0;
+  const int grid =
+      PersistentGrid(reinterpret_cast<const void*>(k), &occ, work_ctas);
+  k<<<grid, kCtaThreads, 0, stream>>>(a);
+  CountLaunch();
+}
+
+// Largest power-of-two <= 16 that divides every value in `bits` (an OR of
+// addresses and pitches).
+int CommonAlign(uint64_t bits) {
+  int v = 16;
+  while (v > 1 && (bits & (v - 1)) != 0) v /= 2;
+  return v;
+}
+
+}  // namespace
+
+int LaunchForward(const void* params, int in_dtype, int embed_width,
+                  const void* indices, int idx_type, const void* offsets,
+                  int off_type, const void* weights, int batch_size,
+                  int num_hots, int mode, int fp16_math, void* ret,
+                  int out_dtype, cudaStream_t stream) {
+  // Same argument checks as the reference host function,
+  // cuembed/include/embedding_lookup.cuh:260-267.
+  if (weights != nullptr && mode == CUEMBED_CONCAT)
+    return CUEMBED_ERR_WEIGHTED_CONCAT;
+  if (!((offsets != nullptr && num_hots == 0) ||
+        (offsets == nullptr && num_hots > 0)))
+    return CUEMBED_ERR_CSR_XOR_FIXED;
+  if (offsets != nullptr && mode == CUEMBED_CONCAT)
+    return CUEMBED_ERR_CSR_CONCAT;
+  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2 ||
+      idx_type < 0 || idx_type > 1 || mode < 0 || mode > 2)
+    return CUEMBED_ERR_DTYPE;
+  if (batch_size < 0 || embed_width <= 0) return CUEMBED_ERR_ARGUMENT;
+  if (batch_size == 0) return CUEMBED_OK;
+  if (params == nullptr || indices == nullptr || ret == nullptr)
+    return CUEMBED_ERR_ARGUMENT;
+  const int64_t row_bytes =
+      static_cast<int64_t>(embed_width) * ElemSize(in_dtype);
+  if (row_bytes % 4 != 0) return CUEMBED_ERR_ROW_BYTES;
+
+  RowShape shape;
+  MakeRowShape(embed_width, in_dtype, &shape);
+
+  if (mode == CUEMBED_CONCAT) {
+    if (out_dtype != in_dtype) return CUEMBED_ERR_DTYPE;
+    // Vector width limited by the actual pointer alignment.
+    int v = CommonAlign(reinterpret_cast<uint64_t>(params) |
+                        reinterpret_cast<uint64_t>(ret) |
+                        static_cast<uint64_t>(row_bytes));
+    if (v > shape.vec_bytes) v = shape.vec_bytes;
+    if (v < 4) return CUEMBED_ERR_ARGUMENT;
+    ConcatArgs c;
+    c.params = params;
+    c.indices = indices;
+    c.out = ret;
+    c.row_bytes = row_bytes;
+    c.nnz = static_cast<int64_t>(batch_size) * num_hots;
+    c.nvec = static_cast<int>(row_bytes / v);
+    c.lanes = Pow2Ceil(c.nvec) < 32 ? Pow2Ceil(c.nvec) : 32;
+    c.log2_lanes = Log2(c.lanes);
+    c.col_tiles = (c.nvec + c.lanes - 1) / c.lanes;
+    if (c.nnz == 0) return CUEMBED_OK;
+#define CONCAT_CASE(VV)                               \
+  if (idx_type == CUEMBED_I64)                        \
+    LaunchConcat<VV, int64_t>(c, stream);             \
+  else                                                \
+    LaunchConcat<VV, int32_t>(c, stream)
+    if (v == 16) {
+      CONCAT_CASE(16);
+    } else if (v == 8) {
+      CONCAT_CASE(8);
+    } else {
+      CONCAT_CASE(4);
+    }
+#undef CONCAT_CASE
+    return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+  }
+
+  // Sum / mean.  The input vector of V bytes holds NE elements; the output
+  // vector holds the same NE elements of the output type.
+  const int64_t out_row_bytes =
+      static_cast<int64_t>(embed_width) * ElemSize(out_dtype);
+  int v = shape.vec_bytes;
+  for (;;) {
+    const uint64_t in_bits =
+        reinterpret_cast<uint64_t>(params) | static_cast<uint64_t>(row_bytes);
+    const int64_t out_vec =
+        static_cast<int64_t>(v) * ElemSize(out_dtype) / ElemSize(in_dtype);
+    const uint64_t out_bits = reinterpret_cast<uint64_t>(ret) |
+                              static_cast<uint64_t>(out_row_bytes);
+    const bool ok = (in_bits % v == 0) &&
+                    (out_bits % (out_vec > 16 ? 16 : out_vec) == 0);
+    if (ok || v == 4) break;
+    v /= 2;
+  }
+  if (v < static_cast<int>(ElemSize(in_dtype)) * 1 || v < 4)
+    return CUEMBED_ERR_ARGUMENT;
+
+  FwdArgs a;
+  a.params = params;
+  a.indices = indices;
+  a.offsets = offsets;
+  a.weights = weights;
+  a.out = ret;
+  a.row_bytes = row_bytes;
+  a.out_row_bytes = out_row_bytes;
+  a.batch = batch_size;
+  a.num_hots = num_hots;
+  a.off64 = (off_type == CUEMBED_I64);
+  a.mean = (mode == CUEMBED_MEAN);
+  a.out_dt = out_dtype;
+  a.nvec = static_cast<int>(row_bytes / v);
+  a.lanes = Pow2Ceil(a.nvec) < 32 ? Pow2Ceil(a.nvec) : 32;
+  a.log2_lanes = Log2(a.lanes);
+  a.col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
+
+  const bool weighted = weights != nullptr;
+  const bool lowp = fp16_math != 0 && in_dtype != CUEMBED_F32;
+  if (in_dtype == CUEMBED_F32)
+    LaunchPoolIdx<float>(a, idx_type, v, weighted, lowp, stream);
+  else if (in_dtype == CUEMBED_F16)
+    LaunchPoolIdx<__half>(a, idx_type, v, weighted, lowp, stream);
+  else
+    LaunchPoolIdx<__nv_bfloat16>(a, idx_type, v, weighted, lowp, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+}
+
+}  // namespace cuembed_b200

@@ -1,0 +1,164 @@
+/*
+ * cuembed_b200.h -- C ABI of the B200-native embedding-lookup library.
+ *
+ * This is the drop-in boundary for the cuEmbed hot path (forward pool ->
+ * index transpose -> backward).  The reference exposes that path as
+ * header-only C++ templates in namespace cuembed; each entry point below is
+ * the type-erased launcher behind one of those templates (file:line refer to
+ * the reference tree, NVIDIA/cuEmbed @ 90dd8436):
+ *
+ *   cuembed_forward                     EmbeddingForward
+ *                                       cuembed/include/embedding_lookup.cuh:245-308
+ *   cuembed_extract_row_ids_fixed       ExtractRowIdsFromFixed
+ *                                       cuembed/include/index_transforms.cuh:45-55
+ *   cuembed_extract_row_ids_csr         ExtractRowIdsFromCSR     :66-74
+ *   cuembed_extract_row_ids_concat      ExtractRowIdsForConcat   :85-93
+ *   cuembed_transpose                   Transpose                :224-250
+ *   cuembed_compressed_grad_indices     ComputeCompressedGradIndices :278-323
+ *   cuembed_backward                    EmbeddingBackward
+ *                                       cuembed/include/embedding_lookup.cuh:423-483
+ *
+ * The C++ templates with the reference's exact signatures live in
+ * include/cuembed/include/{embedding_lookup,index_transforms}.cuh and forward
+ * to these functions; INTEGRATION.md shows both bindings.
+ *
+ * Conventions (same as the reference, cuembed/README.md):
+ *   - every pointer is caller-owned DEVICE (or managed) memory unless named
+ *     lwork; nothing here synchronises; all work is enqueued on `stream`;
+ *   - scratch memory is caller-provided through the work/lwork two-call query
+ *     (call with work == NULL to get the size in *lwork);
+ *   - functions return CUEMBED_OK or a negative error code instead of
+ *     aborting; the C++ templates turn a non-zero code into the reference's
+ *     "Check failed ... abort()" behaviour.
+ * There is no CPU fallback: every call launches sm_100a kernels.
+ */
+#ifndef CUEMBED_B200_H_
+#define CUEMBED_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without dragging cuda_runtime.h into C callers. */
+typedef struct CUstream_st* cuembed_stream_t;
+
+/* element dtype codes */
+#define CUEMBED_F32 0
+#define CUEMBED_F16 1
+#define CUEMBED_BF16 2
+/* index / offset type codes */
+#define CUEMBED_I32 0
+#define CUEMBED_I64 1
+/* combine modes, same order as cuembed::CombineMode
+ * (cuembed/include/embedding_lookup_types.cuh:29) */
+#define CUEMBED_SUM 0
+#define CUEMBED_MEAN 1
+#define CUEMBED_CONCAT 2
+
+/* error codes */
+#define CUEMBED_OK 0
+#define CUEMBED_ERR_WEIGHTED_CONCAT (-1) /* embedding_lookup.cuh:260-261 */
+#define CUEMBED_ERR_CSR_XOR_FIXED (-2)   /* embedding_lookup.cuh:263-265 */
+#define CUEMBED_ERR_CSR_CONCAT (-3)      /* embedding_lookup.cuh:266-267 */
+#define CUEMBED_ERR_ROW_BYTES (-4)       /* row bytes % 4, :163 */
+#define CUEMBED_ERR_DTYPE (-5)           /* unsupported dtype combination */
+#define CUEMBED_ERR_WORKSPACE (-6)       /* *lwork too small, index_transforms.cuh:126 */
+#define CUEMBED_ERR_ARGUMENT (-7)        /* null / negative argument */
+#define CUEMBED_ERR_CUDA (-8)            /* a CUDA runtime call failed */
+#define CUEMBED_ERR_NNZ_LIMIT (-9)       /* nnz >= 2^30 in transpose */
+
+/* Library / ABI version and the SM architecture the kernels were built for. */
+int cuembed_version(void);
+const char* cuembed_build_arch(void);
+const char* cuembed_error_string(int code);
+
+/*
+ * Pooled embedding lookup.  params [rows, embed_width] row-major of in_dtype;
+ * indices [nnz] of idx_type; offsets [batch_size + 1] of off_type (CSR) or
+ * NULL with num_hots > 0 (fixed hotness); weights [nnz] of in_dtype or NULL;
+ * ret [batch_size, embed_width] of out_dtype (sum / mean) or
+ * [nnz, embed_width] of in_dtype (concat).  fp16_math != 0 accumulates in the
+ * input type (meaningful for F16/BF16 only).  Accumulation is sequential in
+ * bag order per output element, so fp32 results are bit-identical to the
+ * reference's CPU implementation.
+ */
+int cuembed_forward(const void* params, int in_dtype, int embed_width,
+                    const void* indices, int idx_type, const void* offsets,
+                    int off_type, const void* weights, int batch_size,
+                    int num_hots, int mode, int fp16_math, void* ret,
+                    int out_dtype, cuembed_stream_t stream);
+
+/* row_ids[i] = i / num_hots, nnz = batch_size * num_hots. */
+int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
+                                  int idx_type, cuembed_stream_t stream);
+/* row_ids[offsets[b] .. offsets[b+1]) = b. */
+int cuembed_extract_row_ids_csr(const void* offsets, int off_type,
+                                int batch_size, void* row_ids, int idx_type,
+                                cuembed_stream_t stream);
+/* row_ids[i] = i. */
+int cuembed_extract_row_ids_concat(int nnz, void* row_ids, int idx_type,
+                                   cuembed_stream_t stream);
+
+/*
+ * Stable sort of the COO triples by `cols` (table index).  rows = sample ids,
+ * weights optional (weight_dtype is the element dtype of weights).
+ * transpose_rows receives the sorted table indices, transpose_cols the sample
+ * ids, transpose_weights the weights.  Two-call workspace protocol.
+ */
+int cuembed_transpose(const void* rows, const void* cols, const void* weights,
+                      int weight_dtype, int nnz, int idx_type,
+                      void* transpose_rows, void* transpose_cols,
+                      void* transpose_weights, char* work, size_t* lwork,
+                      cuembed_stream_t stream);
+
+/* Dense rank of each element of a grouped index array:
+ * [4,4,7,8,8,8,18] -> [0,0,1,2,2,2,3].  Two-call workspace protocol. */
+int cuembed_compressed_grad_indices(const void* indices, int idx_type, int nnz,
+                                    void* remapped_indices, char* work,
+                                    size_t* lwork, cuembed_stream_t stream);
+
+/*
+ * Gradient w.r.t. the table: grad_embedding[r] = sum over the run of equal
+ * transpose_indices of weight * grad_y[sample].  Deterministic: fp32
+ * accumulation in a fixed order, one rounding to `dtype` per output element,
+ * no atomics.  transpose_remapped_indices != NULL selects compressed
+ * gradients and fills inverse_mapping.  skip_grad_init == 0 zero-fills
+ * grad_embedding first; with skip_grad_init != 0 rows that receive a gradient
+ * are overwritten and all other rows are left untouched.
+ *
+ * cuembed_backward takes its scratch (a few MB of partial sums for runs that
+ * span thread blocks) from a library-owned stream-ordered memory pool, because
+ * the reference signature has no workspace argument.
+ * cuembed_backward_ws is the same operation with caller-provided scratch
+ * (two-call protocol) for callers that must not allocate.
+ */
+int cuembed_backward(const void* grad_y, int dtype, int embed_width,
+                     int num_grad_embedding_rows, int nnz, int idx_type,
+                     const void* transpose_indices,
+                     const void* transpose_sample_ids,
+                     const void* transpose_remapped_indices,
+                     const void* transpose_weights, int skip_grad_init,
+                     void* grad_embedding, void* inverse_mapping,
+                     cuembed_stream_t stream);
+
+int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
+                        int num_grad_embedding_rows, int nnz, int idx_type,
+                        const void* transpose_indices,
+                        const void* transpose_sample_ids,
+                        const void* transpose_remapped_indices,
+                        const void* transpose_weights, int skip_grad_init,
+                        void* grad_embedding, void* inverse_mapping,
+                        char* work, size_t* lwork, cuembed_stream_t stream);
+
+/* Number of kernels this library has launched in this process (all threads);
+ * used by bench.py to report `gpu_launches`. */
+unsigned long long cuembed_launch_count(void);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* CUEMBED_B200_H_ */
