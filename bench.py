@@ -1,0 +1,530 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the embedding hot path on B200.
+
+A "step" is one pass of the hot path over one synthetic batch:
+    forward pool  ->  index transpose (row ids + sort + compressed remap)
+                  ->  backward (compressed gradient)
+on the manual_benchmark default workload of the reference (README.md:104):
+10 M x 256 fp16 table, batch 65536, hotness 64, alpha 1.15, int32 indices,
+fixed hotness, unweighted sum, compressed gradient, skip_grad_init.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  Stage times are CUDA-event times on the
+launching stream with an L2 flush (write of a 512 MB buffer) before every
+stage, so no stage starts with its inputs cached by the previous one --
+the reference's protocol (benchmarks/manual_benchmark.cu:199-248).
+Algorithmic bytes per stage are the reference's own formulas
+(benchmarks/manual_benchmark.cu:250-261,340-354,444-473); see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ----------------------------------------------------------------- workload
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "C2": dict(num_categories=10_000_000, embed_width=256, batch_size=65536,
+               hotness=64, alpha=1.15, dtype="f16", index="int32"),
+    # BASELINE.json configs[0] (CPU reference check shape)
+    "C1": dict(num_categories=1_048_576, embed_width=32, batch_size=1024,
+               hotness=8, alpha=0.0, dtype="f32", index="int32"),
+    # small shape for smoke runs
+    "tiny": dict(num_categories=100_000, embed_width=256, batch_size=4096,
+                 hotness=64, alpha=1.15, dtype="f16", index="int32"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def stage_bytes(cfg, nnz, num_unique):
+    """Algorithmic bytes per stage, the reference's accounting."""
+    es = 2 if cfg["dtype"] in ("f16", "bf16") else 4
+    isz = 4 if cfg["index"] == "int32" else 8
+    w, b = cfg["embed_width"], cfg["batch_size"]
+    fwd = es * w * (nnz + b)                                   # manual_benchmark.cu:256-260
+    tr = nnz * isz * (1 + 3)                                   # :340-354, compressed
+    bwd_dram = es * w * num_unique + 2 * isz * nnz + es * w * b  # :451-467
+    bwd_l2 = bwd_dram + es * w * nnz                           # :468-473
+    return dict(forward=fwd, transpose=tr, backward=bwd_l2, backward_dram=bwd_dram)
+
+
+# ------------------------------------------------------------ CPU baselines
+def cpu_reference_pass(cfg, wl_indices, table_host, grad_y_host, sample_bags,
+                       threads, kind):
+    """One pass of the reference CPU path on the first `sample_bags` bags.
+    Returns (seconds per stage dict, sample nnz)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu_lib
+    lib = cpu_lib.CpuLib(kind)
+    hot, w = cfg["hotness"], cfg["embed_width"]
+    nnz = sample_bags * hot
+    idx = np.ascontiguousarray(wl_indices[:nnz])
+    t = {}
+    ret = cpu_lib.empty_like_dt((sample_bags, w), cpu_lib.dt_code(table_host))
+    bounds = np.linspace(0, sample_bags, threads + 1).astype(int)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: lib.forward(
+            table_host, idx, None, None, sample_bags, hot, cpu_lib.SUM,
+            embed_width=w, ret=ret, sample_begin=int(bounds[i]),
+            sample_end=int(bounds[i + 1])), range(threads)))
+    t["forward"] = time.perf_counter() - t0
+    # transpose: single-threaded in the reference (std::sort of tuples)
+    t0 = time.perf_counter()
+    rows = lib.extract_row_ids_fixed(sample_bags, hot, idx.dtype)
+    t_idx, t_sid, _ = lib.transpose(rows, idx, None)
+    remapped = lib.compressed_grad_indices(t_idx)
+    t["transpose"] = time.perf_counter() - t0
+    num_unique = int(remapped[-1]) + 1
+    grad = cpu_lib.empty_like_dt((num_unique, w), cpu_lib.dt_code(grad_y_host))
+    inv = np.zeros(num_unique, idx.dtype)
+    # backward sliced at run boundaries across threads (pointer offsets only)
+    cuts = [0]
+    for i in range(1, threads):
+        c = int(nnz * i / threads)
+        while c < nnz and c > 0 and t_idx[c] == t_idx[c - 1]:
+            c += 1
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(nnz)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: lib.backward(
+            grad_y_host, w, num_unique, t_idx, t_sid, remapped, None,
+            skip_grad_init=True, grad_embedding=grad, inverse_mapping=inv,
+            nz_begin=cuts[i], nz_end=cuts[i + 1]) if cuts[i + 1] > cuts[i] else None,
+            range(threads)))
+    t["backward"] = time.perf_counter() - t0
+    return t, nnz
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_kind():
+    from oracle import cpu_lib
+    if cpu_lib.ref_available():
+        return "ref", "reference"
+    cpu_lib.build(ref=False)
+    return "oracle", "port"
+
+
+def make_host_inputs(cfg, sample_bags, seed=1234):
+    """Host arrays for the CPU legs: full index list + table + grad_y sample."""
+    from cuembed_b200 import datagen
+    idt = np.int32 if cfg["index"] == "int32" else np.int64
+    # The index list is deterministic (fixed seed); cache it between runs of the
+    # same box session to keep parameter sweeps short.
+    key = "_".join(str(cfg[k]) for k in ("num_categories", "batch_size", "hotness", "alpha", "index"))
+    cache = os.path.join("/tmp", f"cuembed_b200_wl_{key}_{seed}.npy")
+    if os.path.exists(cache):
+        idx = np.load(cache)
+        return datagen.Workload(cfg["num_categories"], cfg["embed_width"], cfg["batch_size"],
+                                cfg["hotness"], idx, None, None, int(idx.shape[0]))
+    wl = datagen.make_workload(cfg["num_categories"], cfg["embed_width"],
+                               cfg["batch_size"], cfg["hotness"],
+                               alpha=cfg["alpha"], seed=seed, index_dtype=idt)
+    try:
+        np.save(cache, wl.indices)
+    except OSError:
+        pass
+    return wl
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_e2e(args, ce, torch, dev, tdt, idt, cfg, idx_host, indices, grad_y, out,
+            t_idx, t_sid, remapped, grad, inv, bwork, num_unique, forward, transpose):
+    """End to end through the public API with HOST buffers: every step copies
+    the indices and grad_y in from pinned memory and reads the pooled output,
+    the compressed gradient and its row list back."""
+    w, batch, hot = cfg["embed_width"], cfg["batch_size"], cfg["hotness"]
+    nnz = batch * hot
+    table_es = 2 if cfg["dtype"] in ("f16", "bf16") else 4
+    gy_host = grad_y.cpu().pin_memory()
+    out_host = torch.empty(batch, w, dtype=tdt).pin_memory()
+    grad_host = torch.empty(num_unique, w, dtype=tdt).pin_memory()
+    inv_host = torch.empty(num_unique, dtype=idt).pin_memory()
+    nu_host = torch.empty(1, dtype=idt).pin_memory()
+
+    def e2e_step():
+        indices.copy_(idx_host, non_blocking=True)
+        forward()
+        out_host.copy_(out, non_blocking=True)
+        grad_y.copy_(gy_host, non_blocking=True)
+        transpose()
+        nu_host.copy_(remapped[-1:], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # caller sizes the gradient
+        nu = int(nu_host.item()) + 1
+        ce.EmbeddingBackward(grad_y, w, nu, nnz, t_idx, t_sid, remapped, None,
+                             True, grad, inv, work=bwork)
+        grad_host[:nu].copy_(grad[:nu], non_blocking=True)
+        inv_host[:nu].copy_(inv[:nu], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    isz = indices.element_size()
+    h2d = nnz * isz + batch * w * table_es
+    d2h = batch * w * table_es + num_unique * w * table_es + num_unique * isz + isz
+    return e2e_ms, h2d, d2h
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import cuembed_b200 as ce
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from cuembed_b200 import sharded_bench
+        return sharded_bench.run(args, rank, local_rank, world)
+
+    cfg = WORKLOADS[args.workload]
+    tdt = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[cfg["dtype"]]
+    idt = torch.int32 if cfg["index"] == "int32" else torch.int64
+    rows, w, batch, hot = (cfg["num_categories"], cfg["embed_width"],
+                           cfg["batch_size"], cfg["hotness"])
+    nnz = batch * hot
+
+    wl = make_host_inputs(cfg, batch)
+    # table U(-1,1), generated on the device (5 GB for C2), seeded
+    g = torch.Generator(device=dev)
+    g.manual_seed(123456)
+    table = torch.empty(rows, w, dtype=tdt, device=dev)
+    chunk = 1 << 20
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        table[r0:r1] = (torch.rand(r1 - r0, w, generator=g, device=dev) * 2 - 1).to(tdt)
+    g.manual_seed(654321)
+    grad_y = torch.randint(-10, 11, (batch, w), generator=g, device=dev).to(tdt)
+
+    idx_host = torch.from_numpy(wl.indices).pin_memory()
+    indices = idx_host.to(dev, non_blocking=True)
+    out = torch.empty(batch, w, dtype=tdt, device=dev)
+    row_ids = torch.empty(nnz, dtype=idt, device=dev)
+    t_idx = torch.empty(nnz, dtype=idt, device=dev)
+    t_sid = torch.empty(nnz, dtype=idt, device=dev)
+    remapped = torch.empty(nnz, dtype=idt, device=dev)
+    lwork = max(ce.Transpose(row_ids, indices, None, nnz, None, None, None, None),
+                ce.ComputeCompressedGradIndices(indices, nnz, None, None))
+    work = torch.empty(lwork, dtype=torch.uint8, device=dev)
+    bwork = torch.empty(ce.backward_workspace_bytes(tdt, w, nnz, idt),
+                        dtype=torch.uint8, device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def forward():
+        ce.EmbeddingForward(table, w, indices, None, None, batch, hot,
+                            ce.CombineMode.kSum, out)
+
+    def transpose():
+        ce.ExtractRowIdsFromFixed(batch, hot, row_ids)
+        ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+        ce.ComputeCompressedGradIndices(t_idx, nnz, remapped, work)
+
+    # first pass to learn num_unique (the caller reads remapped.back()+1 on the
+    # host, benchmarks/manual_benchmark.cu:392-394)
+    forward()
+    transpose()
+    num_unique = int(remapped[-1].item()) + 1
+    grad = torch.zeros(num_unique, w, dtype=tdt, device=dev)
+    inv = torch.empty(num_unique, dtype=idt, device=dev)
+
+    def backward():
+        ce.EmbeddingBackward(grad_y, w, num_unique, nnz, t_idx, t_sid, remapped,
+                             None, True, grad, inv, work=bwork)
+
+    stages = [("forward", forward), ("transpose", transpose), ("backward", backward)]
+    stream = torch.cuda.current_stream()
+
+    def one_step(times=None):
+        for name, fn in stages:
+            flush.fill_(1)  # L2 flush: 512 MB write > 126 MB L2
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            if times is not None:
+                times.append((name, e0, e1))
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ce.launch_count()
+    events = []
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(events)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ce.launch_count() - launches0
+    per_stage = {"forward": 0.0, "transpose": 0.0, "backward": 0.0}
+    for name, e0, e1 in events:
+        per_stage[name] += e0.elapsed_time(e1)
+    for k in per_stage:
+        per_stage[k] /= args.steps
+    ms_per_step = sum(per_stage.values())
+
+    e2e_ms, h2d, d2h = float("nan"), 0, 0
+    if not args.no_e2e:
+        e2e_ms, h2d, d2h = run_e2e(args, ce, torch, dev, tdt, idt, cfg, idx_host, indices,
+                                   grad_y, out, t_idx, t_sid, remapped, grad, inv, bwork,
+                                   num_unique, forward, transpose)
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel (one launch per stage for fwd; the
+    # backward stage is the segmented-reduce kernel + a small fix-up kernel)
+    peak, peak_src = measured_peaks()
+    by = stage_bytes(cfg, nnz, num_unique)
+    dominant = max(("forward", "backward"), key=lambda k: per_stage[k])
+    kernel_name = {"forward": "FwdPoolKernel", "backward": "BwdSegReduceKernel"}[dominant]
+    achieved = by[dominant] / (per_stage[dominant] * 1e-3) / 1e9
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of
+    # this same workload (profiles/*_ncu_summary.json), per launch.
+    traffic = None
+    if args.workload == "C2":
+        summaries = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles"))
+                           if f.endswith("_ncu_summary.json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+        if summaries:
+            with open(os.path.join(ROOT, "profiles", summaries[-1])) as f:
+                summ = json.load(f)
+            if kernel_name in summ and "dram_bytes" in summ[kernel_name]:
+                traffic = int(summ[kernel_name]["dram_bytes"])
+    roofline = {"bound": "hbm", "kernel": kernel_name, "stage": dominant,
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": by[dominant]}
+    agg_bytes = by["forward"] + by["transpose"] + by["backward"]
+    stage_report = {k: {"ms": round(per_stage[k], 4),
+                        "lookups_per_s": round(nnz / (per_stage[k] * 1e-3), 1),
+                        "algo_GBps": round(by[k] / (per_stage[k] * 1e-3) / 1e9, 1),
+                        "frac_of_hbm_peak": round(by[k] / (per_stage[k] * 1e-3) / 1e9 / peak, 4)}
+                    for k in per_stage}
+    stage_report["aggregate"] = {
+        "algo_GBps": round(agg_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+        "frac_of_hbm_peak": round(agg_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if not args.no_cpu_baseline:
+        kind_lib, kind = cpu_kind()
+        sample_bags = min(batch, args.cpu_sample_bags)
+        threads = host_threads()
+        table_host = table.cpu().numpy() if tdt != torch.bfloat16 else None
+        gyh = grad_y.cpu().numpy() if tdt != torch.bfloat16 else None
+        if table_host is None:
+            from oracle.cpu_lib import Bf16
+            table_host = Bf16(table.view(torch.int16).cpu().numpy().view(np.uint16))
+            gyh = Bf16(grad_y.view(torch.int16).cpu().numpy().view(np.uint16))
+        t, s_nnz = cpu_reference_pass(cfg, wl.indices, table_host, gyh,
+                                      sample_bags, threads, kind_lib)
+        total = sum(t.values())
+        cpu = {"value": round(s_nnz / total, 1), "unit": "lookups/s",
+               "cores": threads, "kind": kind,
+               "sample": f"first {sample_bags} of {batch} bags ({s_nnz} lookups), "
+                         f"fwd+transpose+bwd once; fwd and bwd sliced over {threads} "
+                         f"threads, transpose single-threaded as in the reference",
+               "stage_s": {k: round(v, 4) for k, v in t.items()}}
+
+    line = {
+        "metric": "lookups/s (fwd + transpose + bwd, compressed grad)",
+        "value": round(nnz / (ms_per_step * 1e-3), 1),
+        "unit": "lookups/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": f"manual_benchmark default ({args.workload}): "
+                               f"{rows}x{w} {cfg['dtype']}, batch {batch}, hotness {hot}, "
+                               f"alpha {cfg['alpha']}, {cfg['index']} indices, sum, compressed grad",
+                   "l2": "flushed before every stage (512 MB write)",
+                   "num_unique": num_unique, "nnz": nnz},
+        "stages": stage_report,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": (round(nnz / (e2e_ms * 1e-3), 1) if e2e_ms == e2e_ms else None),
+                "unit": "lookups/s",
+                "ms_per_step": (round(e2e_ms, 4) if e2e_ms == e2e_ms else None),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "wall_s_timed_region": round(t_wall, 3),
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    kind_lib, kind = cpu_kind()
+    threads = host_threads()
+    batch = cfg["batch_size"]
+    sample_bags = min(batch, args.cpu_sample_bags)
+    wl = make_host_inputs(cfg, batch)
+    from cuembed_b200 import datagen
+    # The CPU path only touches the rows its sample references, but the table
+    # must exist at full size for the indices to be valid.
+    rng = np.random.default_rng(123456)
+    dt = np.float16 if cfg["dtype"] == "f16" else np.float32
+    table = np.empty((cfg["num_categories"], cfg["embed_width"]), dt)
+    step_rows = 1 << 20
+    for r0 in range(0, cfg["num_categories"], step_rows):
+        r1 = min(cfg["num_categories"], r0 + step_rows)
+        table[r0:r1] = (rng.random((r1 - r0, cfg["embed_width"]), dtype=np.float32) * 2 - 1).astype(dt)
+    grad_y = datagen.make_grad_y(batch, cfg["embed_width"]).astype(dt)
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_pass(cfg, wl.indices, table, grad_y, sample_bags, threads, kind_lib)
+    tot = 0.0
+    stage = {"forward": 0.0, "transpose": 0.0, "backward": 0.0}
+    s_nnz = 0
+    for _ in range(args.steps):
+        t, s_nnz = cpu_reference_pass(cfg, wl.indices, table, grad_y, sample_bags,
+                                      threads, kind_lib)
+        tot += sum(t.values())
+        for k in stage:
+            stage[k] += t[k]
+    ms = tot / args.steps * 1e3
+    value = s_nnz / (ms * 1e-3)
+    sample = (f"first {sample_bags} of {batch} bags ({s_nnz} lookups) per step; fwd and bwd "
+              f"sliced over {threads} threads, transpose single-threaded as in the reference")
+    line = {
+        "impl": "reference",
+        "metric": "lookups/s (fwd + transpose + bwd, compressed grad)",
+        "value": round(value, 1), "unit": "lookups/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": f"manual_benchmark default ({args.workload}), CPU reference path "
+                               f"({'oracle/_ref: reference templates' if kind == 'reference' else 'oracle port'})",
+                   "sample": sample},
+        "cpu_baseline": {"value": round(value, 1), "unit": "lookups/s", "cores": threads,
+                         "kind": kind, "sample": sample,
+                         "stage_s": {k: round(v / args.steps, 4) for k, v in stage.items()}},
+        "e2e": {"value": round(value, 1), "unit": "lookups/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-bags", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -177,25 +177,31 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
         // harmless load that is never accumulated.
         vals[u] = LdgVec<V>(gy + GradRowOffset<IdxT>(s, row_bytes));
       }
+      // Fast path: a full batch in which no lane group of the warp ends a run
+      // (the interior of long runs, ~half of all nonzeros under a power law).
+      if constexpr (UNROLL <= 8) {
+        const unsigned batch_bits = (patt * ((1u << UNROLL) - 1u)) << jb;
+        if (G >= UNROLL && (endsw & batch_bits) == 0u &&
+            __all_sync(kFull, jb + UNROLL <= cnt)) {
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            if constexpr (WEIGHTED)
+              AccumulateVecWeighted<T, V>(vals[u], Elem<T>::ToFloat(wv[u]), acc);
+            else
+              AccumulateVec<T, V>(vals[u], acc);
+          }
+          open = true;
+          continue;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int j = jb + u;
         if (j < cnt) {
-          uint32_t wd[NW];
-          Unpack32(vals[u], wd);
-#pragma unroll
-          for (int q = 0; q < NW; ++q) {
-            float f[Elem<T>::kPerWord];
-            Elem<T>::WordToFloat(wd[q], f);
-#pragma unroll
-            for (int k = 0; k < Elem<T>::kPerWord; ++k) {
-              float& x = acc[q * Elem<T>::kPerWord + k];
-              if constexpr (WEIGHTED)
-                x = __fadd_rn(x, __fmul_rn(f[k], Elem<T>::ToFloat(wv[u])));
-              else
-                x = __fadd_rn(x, f[k]);
-            }
-          }
+          if constexpr (WEIGHTED)
+            AccumulateVecWeighted<T, V>(vals[u], Elem<T>::ToFloat(wv[u]), acc);
+          else
+            AccumulateVec<T, V>(vals[u], acc);
           open = true;
         }
         // Warp-uniform test: does any lane group of this warp end a run at j?
@@ -327,22 +333,50 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
 }
 
 // Adds, in CTA order, the partials of every run that crosses CTA edges:
-// tail of the CTA where the run starts + heads of the following CTAs.
+// tail of the CTA where the run starts + heads of the following CTAs.  The
+// chain length is found first (all threads scan the head kinds), so the loads
+// of the partial rows are independent and issued eight at a time.
 template <typename T>
 __global__ void __launch_bounds__(kCtaThreads)
     BwdFixupKernel(const BwdArgs a) {
+  __shared__ int s_len;
   const int cta = blockIdx.x;
   if (a.meta[cta * 2 + 1] == 0) return;
-  const int col = blockIdx.y * kCtaThreads + threadIdx.x;
-  if (col >= a.width) return;
-  float acc = a.scratch[(static_cast<size_t>(cta) * 2 + 1) * a.width + col];
-  for (int c = cta + 1; c < a.num_ctas; ++c) {
-    const int kind = a.meta[c * 2 + 0];
-    if (kind == kHeadNone) break;
-    acc = __fadd_rn(acc,
-                    a.scratch[(static_cast<size_t>(c) * 2 + 0) * a.width + col]);
-    if (kind == kHeadEnds) break;
+  const int tid = threadIdx.x;
+  // chain = CTAs cta+1 .. cta+len; the last one has kind "ends".
+  if (tid == 0) s_len = 0x7fffffff;
+  __syncthreads();
+  for (int base = cta + 1; base < a.num_ctas; base += kCtaThreads) {
+    const int c = base + tid;
+    if (c < a.num_ctas && a.meta[c * 2 + 0] != kHeadThrough)
+      atomicMin(&s_len, c - cta);
+    __syncthreads();
+    if (s_len != 0x7fffffff) break;
   }
+  __syncthreads();
+  int len = s_len;
+  if (len == 0x7fffffff) len = a.num_ctas - 1 - cta;  // malformed input guard
+  // a "none" head at the end of the chain means the run ended exactly at the
+  // CTA edge (cannot happen for a tail, kept as a guard): exclude it.
+  if (cta + len < a.num_ctas && a.meta[(cta + len) * 2 + 0] == kHeadNone) --len;
+
+  const int col = blockIdx.y * kCtaThreads + tid;
+  if (col >= a.width) return;
+  const float* scratch = a.scratch;
+  const size_t pitch = static_cast<size_t>(2) * a.width;
+  float acc = scratch[static_cast<size_t>(cta) * pitch + a.width + col];
+  int c = cta + 1;
+  const int end = cta + len;  // inclusive
+  for (; c + 7 <= end; c += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = scratch[static_cast<size_t>(c + u) * pitch + col];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
+  }
+  for (; c <= end; ++c)
+    acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
   const long long row = a.meta_row[cta * 2 + 1];
   StoreOneAs<T>(static_cast<T*>(a.grad) + row * a.width + col, acc);
 }

@@ -205,6 +205,70 @@ struct Elem<__nv_bfloat16> {
   }
 };
 
+// acc0 += lo half, acc1 += hi half of a packed 16-bit pair, in fp32 with one
+// rounding per add.  sm_100a has a mixed-precision add (SASS FHADD), so this is
+// ONE instruction per element instead of convert + add; the result is
+// bit-identical because widening to fp32 is exact.
+template <typename T>
+__device__ __forceinline__ void AddPairF32(uint32_t w, float& acc0, float& acc1);
+template <>
+__device__ __forceinline__ void AddPairF32<__half>(uint32_t w, float& acc0,
+                                                   float& acc1) {
+  asm("{.reg .f16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.rn.f32.f16 %0, lo, %0;\n\t"
+      "add.rn.f32.f16 %1, hi, %1;}"
+      : "+f"(acc0), "+f"(acc1)
+      : "r"(w));
+}
+template <>
+__device__ __forceinline__ void AddPairF32<__nv_bfloat16>(uint32_t w,
+                                                          float& acc0,
+                                                          float& acc1) {
+  asm("{.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.rn.f32.bf16 %0, lo, %0;\n\t"
+      "add.rn.f32.bf16 %1, hi, %1;}"
+      : "+f"(acc0), "+f"(acc1)
+      : "r"(w));
+}
+
+// acc[NE] += the NE elements packed in the V-byte vector `v` (fp32 adds).
+template <typename T, int V>
+__device__ __forceinline__ void AccumulateVec(typename VecBits<V>::type v,
+                                              float* acc) {
+  constexpr int NW = V / 4;
+  uint32_t w[NW];
+  Unpack32(v, w);
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = __fadd_rn(acc[i], __uint_as_float(w[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) AddPairF32<T>(w[i], acc[2 * i], acc[2 * i + 1]);
+  }
+}
+
+// acc[NE] += weight * element, multiply and add rounded separately (matches the
+// reference CPU loops for any weight value; no FMA contraction).
+template <typename T, int V>
+__device__ __forceinline__ void AccumulateVecWeighted(
+    typename VecBits<V>::type v, float wf, float* acc) {
+  constexpr int NW = V / 4;
+  uint32_t w[NW];
+  Unpack32(v, w);
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    float f[Elem<T>::kPerWord];
+    Elem<T>::WordToFloat(w[i], f);
+#pragma unroll
+    for (int k = 0; k < Elem<T>::kPerWord; ++k) {
+      float& a = acc[i * Elem<T>::kPerWord + k];
+      a = __fadd_rn(a, __fmul_rn(f[k], wf));
+    }
+  }
+}
+
 // Convert NW accumulator words' worth of floats to an output vector of dtype
 // `out_dt` (runtime) and store it.  `acc` holds NE floats where the INPUT type
 // packs NE elements in V_IN bytes; the output vector has NE elements of the

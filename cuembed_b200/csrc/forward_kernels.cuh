@@ -40,36 +40,13 @@ struct Accum<T, V, false> {
     for (int i = 0; i < NE; ++i) acc[i] = 0.f;
   }
   __device__ __forceinline__ void Add(typename VecBits<V>::type v) {
-    uint32_t w[NW];
-    Unpack32(v, w);
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      float f[Elem<T>::kPerWord];
-      Elem<T>::WordToFloat(w[i], f);
-#pragma unroll
-      for (int k = 0; k < Elem<T>::kPerWord; ++k) {
-        float& a = acc[i * Elem<T>::kPerWord + k];
-        a = __fadd_rn(a, f[k]);
-      }
-    }
+    AccumulateVec<T, V>(v, acc);
   }
   // Separate multiply and add (no FMA contraction): matches the reference CPU
   // loop, utils/include/embedding_lookup_cpu.hpp:73-75, for any weight value.
   __device__ __forceinline__ void AddWeighted(typename VecBits<V>::type v,
                                               T weight) {
-    const float wf = Elem<T>::ToFloat(weight);
-    uint32_t w[NW];
-    Unpack32(v, w);
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      float f[Elem<T>::kPerWord];
-      Elem<T>::WordToFloat(w[i], f);
-#pragma unroll
-      for (int k = 0; k < Elem<T>::kPerWord; ++k) {
-        float& a = acc[i * Elem<T>::kPerWord + k];
-        a = __fadd_rn(a, __fmul_rn(f[k], wf));
-      }
-    }
+    AccumulateVecWeighted<T, V>(v, Elem<T>::ToFloat(weight), acc);
   }
   __device__ __forceinline__ void Scale(float s) {
 #pragma unroll

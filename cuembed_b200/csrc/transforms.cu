@@ -36,13 +36,32 @@ namespace cuembed_b200 {
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kCtaThreads)
-    RowIdsFixedKernel(IdxT* __restrict__ row_ids, int64_t nnz, int num_hots) {
-  // nnz is an int in the API, so 32-bit unsigned division is enough.
-  const uint32_t stride = gridDim.x * blockDim.x;
+    RowIdsFixedKernel(IdxT* __restrict__ row_ids, int64_t nnz, int num_hots,
+                      bool vec_ok) {
+  // nnz is an int in the API, so 32-bit unsigned arithmetic is enough.  Each
+  // thread produces 16 bytes (one vector store) per iteration.
+  constexpr uint32_t PER = 16 / sizeof(IdxT);
   const uint32_t n = static_cast<uint32_t>(nnz);
   const uint32_t h = static_cast<uint32_t>(num_hots);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    row_ids[i] = static_cast<IdxT>(i / h);
+  const uint32_t stride = gridDim.x * blockDim.x * PER;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * PER; i < n;
+       i += stride) {
+    uint32_t q = i / h;
+    uint32_t r = i - q * h;
+    IdxT v[PER];
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) {
+      v[k] = static_cast<IdxT>(q);
+      if (++r == h) {
+        r = 0;
+        ++q;
+      }
+    }
+    if (vec_ok && i + PER <= n) {
+      *reinterpret_cast<uint4*>(row_ids + i) = *reinterpret_cast<uint4*>(v);
+    } else {
+      for (uint32_t k = 0; i + k < n; ++k) row_ids[i + k] = v[k];
+    }
   }
 }
 
@@ -86,13 +105,14 @@ int LaunchExtractRowIdsFixed(int batch_size, int num_hots, void* row_ids,
   const int64_t nnz = static_cast<int64_t>(batch_size) * num_hots;
   if (nnz == 0) return CUEMBED_OK;
   if (row_ids == nullptr) return CUEMBED_ERR_ARGUMENT;
-  const int grid = StreamGrid(nnz);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(row_ids) & 15) == 0;
+  const int grid = StreamGrid(nnz / 2);
   if (idx_type == CUEMBED_I64)
     RowIdsFixedKernel<int64_t><<<grid, kCtaThreads, 0, stream>>>(
-        static_cast<int64_t*>(row_ids), nnz, num_hots);
+        static_cast<int64_t*>(row_ids), nnz, num_hots, vec_ok);
   else
     RowIdsFixedKernel<int32_t><<<grid, kCtaThreads, 0, stream>>>(
-        static_cast<int32_t*>(row_ids), nnz, num_hots);
+        static_cast<int32_t*>(row_ids), nnz, num_hots, vec_ok);
   CountLaunch();
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
@@ -146,35 +166,70 @@ __device__ __forceinline__ uint32_t DigitOf(KeyT key, int pos) {
 }
 
 // Histograms of every byte position in one read of the keys.
-// hist layout: [sizeof(KeyT)][256] uint32.
+// hist layout: [sizeof(KeyT)][256] uint32.  Each thread takes 16 keys per
+// iteration (16 independent coalesced loads in flight); a byte position on
+// which all 512 keys of the warp agree (the usual case for the high bytes)
+// costs one aggregated shared-memory atomic instead of 512.
 template <typename KeyT>
 __global__ void __launch_bounds__(kCtaThreads)
     RadixHistKernel(const KeyT* __restrict__ keys, int nnz,
-                    uint32_t* __restrict__ hist) {
+                    uint32_t* __restrict__ hist,
+                    uint32_t* __restrict__ done_counter,
+                    int* __restrict__ plan) {
   constexpr int ND = sizeof(KeyT);
+  constexpr int ITEMS = 16;
+  constexpr int TILE = ITEMS * kCtaThreads;
+  using U = typename std::conditional<sizeof(KeyT) == 8, uint64_t, uint32_t>::type;
   __shared__ uint32_t sh[ND * kRadix];
   for (int i = threadIdx.x; i < ND * kRadix; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int stride = gridDim.x * blockDim.x;
-  const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  // Warp-synchronous trip count (the condition only depends on the warp's
-  // first index) so that the shuffles below are convergent.
-  for (int i = first; i - lane < nnz; i += stride) {
-    const bool valid = i < nnz;
-    const KeyT key = valid ? __ldg(keys + i) : KeyT(0);
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  const int num_tiles = (nnz + TILE - 1) / TILE;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int base = t * TILE + threadIdx.x;
+    KeyT key[ITEMS];
+    bool full = (t + 1) * static_cast<int64_t>(TILE) <= nnz;
+    if (full) {
 #pragma unroll
-    for (int p = 0; p < ND; ++p) {
-      const uint32_t d = DigitOf<KeyT>(key, p);
-      // Constant (or warp-uniform) digits are the common case for the high
-      // bytes: one aggregated add instead of 32 same-address atomics.
-      const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(vmask) - 1);
-      const bool uniform = __all_sync(0xffffffffu, !valid || d == d0);
-      if (uniform) {
-        if (lane == 0) atomicAdd(&sh[p * kRadix + d0], __popc(vmask));
-      } else if (valid) {
-        atomicAdd(&sh[p * kRadix + d], 1u);
+      for (int i = 0; i < ITEMS; ++i) key[i] = __ldg(keys + base + i * kCtaThreads);
+      // bits on which the keys of this warp differ
+      U diff = 0;
+#pragma unroll
+      for (int i = 1; i < ITEMS; ++i)
+        diff |= static_cast<U>(key[i]) ^ static_cast<U>(key[0]);
+      const U k0 = static_cast<U>(
+          sizeof(KeyT) == 8
+              ? static_cast<U>(__shfl_sync(0xffffffffu,
+                                           static_cast<long long>(key[0]), 0))
+              : static_cast<U>(__shfl_sync(0xffffffffu,
+                                           static_cast<int>(key[0]), 0)));
+      diff |= static_cast<U>(key[0]) ^ k0;
+      uint32_t dlo = static_cast<uint32_t>(diff);
+      uint32_t dhi = sizeof(KeyT) == 8 ? static_cast<uint32_t>(static_cast<uint64_t>(diff) >> 32) : 0u;
+      dlo = __reduce_or_sync(0xffffffffu, dlo);
+      if (sizeof(KeyT) == 8) dhi = __reduce_or_sync(0xffffffffu, dhi);
+#pragma unroll
+      for (int p = 0; p < ND; ++p) {
+        const uint32_t byte_diff =
+            (p < 4 ? (dlo >> (8 * p)) : (dhi >> (8 * (p - 4)))) & 0xffu;
+        if (byte_diff == 0) {
+          if (lane == 0)
+            atomicAdd(&sh[p * kRadix + DigitOf<KeyT>(key[0], p)], 32u * ITEMS);
+        } else {
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i)
+            atomicAdd(&sh[p * kRadix + DigitOf<KeyT>(key[i], p)], 1u);
+        }
+      }
+    } else {
+      for (int i = 0; i < ITEMS; ++i) {
+        const int g = base + i * kCtaThreads;
+        if (g < nnz) {
+          const KeyT k = __ldg(keys + g);
+#pragma unroll
+          for (int p = 0; p < ND; ++p)
+            atomicAdd(&sh[p * kRadix + DigitOf<KeyT>(k, p)], 1u);
+        }
       }
     }
   }
@@ -182,6 +237,55 @@ __global__ void __launch_bounds__(kCtaThreads)
   for (int i = threadIdx.x; i < ND * kRadix; i += blockDim.x) {
     const uint32_t c = sh[i];
     if (c != 0) atomicAdd(&hist[i], c);
+  }
+
+  // ---- the last CTA to finish turns the histograms into the pass plan:
+  //   plan[0] = bit mask of live byte positions (a position where every key has
+  //             the same byte needs no pass), plan[1] = number of live passes;
+  //   hist[p][d] is replaced by its exclusive prefix sum over d (the global
+  //   start of digit d in pass p).  One warp per byte position.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5;
+  __shared__ int s_live[ND];
+  if (warp < ND) {
+    const int p = warp;
+    uint32_t c[8];
+    uint32_t sum = 0;
+    bool degenerate = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c[k] = __ldcg(&hist[p * kRadix + lane * 8 + k]);
+      degenerate |= c[k] == static_cast<uint32_t>(nnz);
+      sum += c[k];
+    }
+    uint32_t scan = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+      if (lane >= o) scan += t;
+    }
+    uint32_t run = scan - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      hist[p * kRadix + lane * 8 + k] = run;
+      run += c[k];
+    }
+    const bool any_deg = __any_sync(0xffffffffu, degenerate);
+    if (lane == 0) s_live[p] = any_deg ? 0 : 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int mask = 0;
+    for (int p = 0; p < ND; ++p) mask |= s_live[p] << p;
+    plan[0] = mask;
+    plan[1] = __popc(static_cast<unsigned>(mask));
   }
 }
 
@@ -200,9 +304,12 @@ struct SortArgs {
   void* keys_tmp;
   void* vals_tmp;
   void* w_tmp;
-  const uint32_t* hist;     // [ND][256]
-  uint32_t* lookback;       // [ND][num_tiles][256], zeroed
-  uint32_t* tile_counters;  // [ND], zeroed
+  const uint32_t* digit_base;  // [ND][256] exclusive digit starts (plan kernel)
+  const int* plan;             // live mask, number of live passes
+  uint32_t* lookback;          // [ND][num_tiles][256], zeroed
+  int tile_pitch;              // unused
+  int debug;                   // tuning experiments only (CUEMBED_SORT_DEBUG)
+  uint32_t* tile_counters;     // [ND], zeroed
   int nnz;
   int num_tiles;
   int pass;  // byte position handled by this launch
@@ -216,15 +323,24 @@ __device__ __forceinline__ uint32_t LdVolatile(const uint32_t* p) {
 __device__ __forceinline__ void StVolatile(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
+__device__ __forceinline__ uint4 LdVolatile4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 
 // One pass of the stable LSD sort over byte position a.pass.
 //   KeyT: int32_t / int64_t (payload sample ids have the same type)
 //   WBYTES: 0 (no weights), 2 or 4 (weight element size)
 //   ITEMS: keys per thread; tile = ITEMS * 256 keys.
+// Persistent CTAs take tiles from a counter; a tile only ever waits for tiles
+// with a smaller id, which were taken earlier, so the look-back cannot
+// deadlock.
 template <typename KeyT, int WBYTES, int ITEMS>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
     RadixPassKernel(const SortArgs a) {
-  constexpr int ND = sizeof(KeyT);
   constexpr int TILE = ITEMS * kCtaThreads;
   using WT = typename std::conditional<WBYTES == 4, uint32_t, uint16_t>::type;
 
@@ -232,41 +348,19 @@ __global__ void __launch_bounds__(kCtaThreads)
   __shared__ uint32_t s_tile_excl[kRadix];  // digit start inside the tile
   __shared__ int32_t s_goff[kRadix];        // global start - tile start
   __shared__ uint32_t s_scan[kWarpsPerCta];
-  __shared__ int s_plan[4];  // live, ordinal, total live passes, tile id
+  __shared__ int s_tile;
   extern __shared__ __align__(16) unsigned char s_exch_raw[];
   KeyT* s_exch = reinterpret_cast<KeyT*>(s_exch_raw);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  // ---- plan: which byte positions are live (derived from the histograms)
-  if (tid < 32) {
-    int live_mask = 0;
-    for (int p = 0; p < ND; ++p) {
-      bool degenerate = false;
-      for (int b = lane; b < kRadix; b += 32)
-        degenerate |= (a.hist[p * kRadix + b] == static_cast<uint32_t>(a.nnz));
-      if (!__any_sync(0xffffffffu, degenerate)) live_mask |= (1 << p);
-    }
-    if (lane == 0) {
-      s_plan[0] = (live_mask >> a.pass) & 1;
-      s_plan[1] = __popc(live_mask & ((1 << a.pass) - 1));
-      s_plan[2] = __popc(live_mask);
-      // Dynamic tile id: a tile only ever waits for tiles that started
-      // earlier, so the look-back cannot deadlock.
-      s_plan[3] = static_cast<int>(atomicAdd(&a.tile_counters[a.pass], 1u));
-    }
-  }
-  for (int i = tid; i < kWarpsPerCta * kRadix; i += kCtaThreads)
-    (&s_warp_cnt[0][0])[i] = 0;
-  __syncthreads();
-  const bool live = s_plan[0] != 0;
-  const int ordinal = s_plan[1];
-  const int total_live = s_plan[2];
-  const int tile = s_plan[3];
-  const int tile_base = tile * TILE;
-  const int tile_n = min(TILE, a.nnz - tile_base);
+  const int live_mask = a.plan[0];
+  const int total_live = a.plan[1];
+  const bool live = ((live_mask >> a.pass) & 1) != 0;
+  const int ordinal = __popc(live_mask & ((1 << a.pass) - 1));
 
   // No live pass at all (all keys equal): pass 0 degenerates to a copy.
   if (total_live == 0) {
@@ -275,12 +369,12 @@ __global__ void __launch_bounds__(kCtaThreads)
     const KeyT* vin = static_cast<const KeyT*>(a.vals_in);
     KeyT* kout = static_cast<KeyT*>(a.keys_out);
     KeyT* vout = static_cast<KeyT*>(a.vals_out);
-    for (int i = tid; i < tile_n; i += kCtaThreads) {
-      kout[tile_base + i] = kin[tile_base + i];
-      vout[tile_base + i] = vin[tile_base + i];
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kCtaThreads + tid;
+         i < a.nnz; i += static_cast<int64_t>(gridDim.x) * kCtaThreads) {
+      kout[i] = kin[i];
+      vout[i] = vin[i];
       if constexpr (WBYTES != 0)
-        static_cast<WT*>(a.w_out)[tile_base + i] =
-            static_cast<const WT*>(a.w_in)[tile_base + i];
+        static_cast<WT*>(a.w_out)[i] = static_cast<const WT*>(a.w_in)[i];
     }
     return;
   }
@@ -308,156 +402,166 @@ __global__ void __launch_bounds__(kCtaThreads)
   KeyT* vout = static_cast<KeyT*>(dst_is_out ? a.vals_out : a.vals_tmp);
   WT* wout = static_cast<WT*>(dst_is_out ? a.w_out : a.w_tmp);
 
-  // ---- load keys: warp-striped so that (warp, item, lane) is input order
-  KeyT key[ITEMS];
-  uint32_t rank[ITEMS];
-  const int warp_base = warp * (32 * ITEMS);
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int local = warp_base + i * 32 + lane;
-    key[i] = local < tile_n ? kin[tile_base + local] : KeyT(0);
-  }
-
-  // ---- stable ranking inside the warp: match-any multisplit
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int local = warp_base + i * 32 + lane;
-    const bool valid = local < tile_n;
-    // Invalid lanes form their own peer group (digit 256) and are ignored.
-    const uint32_t d = valid ? DigitOf<KeyT>(key[i], a.pass) : kRadix;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (valid && lane == leader)
-      old = atomicAdd(&s_warp_cnt[warp][d], __popc(peers));
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = old + __popc(peers & ((1u << lane) - 1u));
-  }
-  __syncthreads();
-
-  // ---- per digit (thread tid owns digit tid): exclusive scan over warps,
-  //      tile total, look-back over earlier tiles
-  uint32_t tile_count = 0;
-#pragma unroll
-  for (int w = 0; w < kWarpsPerCta; ++w) {
-    const uint32_t c = s_warp_cnt[w][tid];
-    s_warp_cnt[w][tid] = tile_count;
-    tile_count += c;
-  }
+  const uint32_t digit_base = a.digit_base[a.pass * kRadix + tid];
   uint32_t* lb = a.lookback +
-                 (static_cast<size_t>(a.pass) * a.num_tiles) * kRadix;
-  if (tile == 0) {
-    StVolatile(&lb[tid], kFlagPrefix | tile_count);
-  } else {
-    StVolatile(&lb[static_cast<size_t>(tile) * kRadix + tid],
-               kFlagAgg | tile_count);
-  }
-  uint32_t exclusive = 0;
-  if (tile > 0) {
-    int prev = tile - 1;
-    while (true) {
-      uint32_t s;
-      do {
-        s = LdVolatile(&lb[static_cast<size_t>(prev) * kRadix + tid]);
-      } while ((s & ~kValueMask) == 0);
-      exclusive += s & kValueMask;
-      if ((s & kFlagPrefix) != 0) break;
-      --prev;
-    }
-    StVolatile(&lb[static_cast<size_t>(tile) * kRadix + tid],
-               kFlagPrefix | (exclusive + tile_count));
-  }
+                 (static_cast<size_t>(a.pass) * a.num_tiles) * kRadix + tid;
+  const int warp_base = warp * (32 * ITEMS);
 
-  // global start of this digit = exclusive scan of the pass histogram
-  // (block-wide scan over the 256 digit owners) + earlier tiles.
-  const uint32_t hcount = a.hist[a.pass * kRadix + tid];
-  uint32_t hscan = hcount, tscan = tile_count;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t h = __shfl_up_sync(0xffffffffu, hscan, o);
-    const uint32_t t = __shfl_up_sync(0xffffffffu, tscan, o);
-    if (lane >= o) {
-      hscan += h;
-      tscan += t;
-    }
-  }
-  __shared__ uint32_t s_hwarp[kWarpsPerCta];
-  if (lane == 31) {
-    s_hwarp[warp] = hscan;
-    s_scan[warp] = tscan;
-  }
-  __syncthreads();
-  uint32_t hbase = 0, tbase = 0;
-#pragma unroll
-  for (int w = 0; w < kWarpsPerCta; ++w) {
-    if (w < warp) {
-      hbase += s_hwarp[w];
-      tbase += s_scan[w];
-    }
-  }
-  const uint32_t h_excl = hbase + hscan - hcount;
-  const uint32_t t_excl = tbase + tscan - tile_count;
-  s_tile_excl[tid] = t_excl;
-  s_goff[tid] = static_cast<int32_t>(h_excl + exclusive) -
-                static_cast<int32_t>(t_excl);
-  __syncthreads();
-
-  // ---- final position of every item inside the tile; keys through smem
-  uint32_t pos[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int local = warp_base + i * 32 + lane;
-    if (local < tile_n) {
-      const uint32_t d = DigitOf<KeyT>(key[i], a.pass);
-      pos[i] = s_tile_excl[d] + s_warp_cnt[warp][d] + rank[i];
-      s_exch[pos[i]] = key[i];
-    } else {
-      pos[i] = 0;
-    }
-  }
-  __syncthreads();
-  int32_t gaddr[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int p = tid + i * kCtaThreads;
-    if (p < tile_n) {
-      const KeyT k = s_exch[p];
-      gaddr[i] = s_goff[DigitOf<KeyT>(k, a.pass)] + p;
-      kout[gaddr[i]] = k;
-    } else {
-      gaddr[i] = -1;
-    }
-  }
-  __syncthreads();
-
-  // ---- payload: sample ids (same type as keys) through the same buffer
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int local = warp_base + i * 32 + lane;
-    if (local < tile_n) s_exch[pos[i]] = vin[tile_base + local];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int p = tid + i * kCtaThreads;
-    if (p < tile_n) vout[gaddr[i]] = s_exch[p];
-  }
-
-  // ---- payload: weights
-  if constexpr (WBYTES != 0) {
+  while (true) {
+    __syncthreads();  // previous tile done with the shared arrays
+    if (tid == 0)
+      s_tile = static_cast<int>(atomicAdd(&a.tile_counters[a.pass], 1u));
+    for (int i = tid; i < kWarpsPerCta * kRadix; i += kCtaThreads)
+      (&s_warp_cnt[0][0])[i] = 0;
     __syncthreads();
-    WT* s_w = reinterpret_cast<WT*>(s_exch_raw);
+    const int tile = s_tile;
+    if (tile >= a.num_tiles) break;
+    const int tile_base = tile * TILE;
+    const int tile_n = min(TILE, a.nnz - tile_base);
+
+    // ---- load keys (payload is loaded after the keys have been scattered: a
+    // software-pipelined variant that prefetched the next tile was measured
+    // slower because it delays the publication of the tile's digit counts,
+    // profiles/r01_notes.md)
+    KeyT key[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       const int local = warp_base + i * 32 + lane;
-      if (local < tile_n) s_w[pos[i]] = win[tile_base + local];
+      key[i] = local < tile_n ? kin[tile_base + local] : KeyT(0);
+    }
+
+    // ---- stable ranking inside the warp.  Items are warp-striped so that
+    // (warp, item, lane) is input order.  The set of lanes holding the same
+    // digit is built from 8 ballots (one per digit bit) -- plain vote / logic
+    // instructions; match.any was measured far slower on this part
+    // (profiles/r01_notes.md).
+    uint32_t rank[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int local = warp_base + i * 32 + lane;
+      const bool valid = local < tile_n;
+      const uint32_t d = DigitOf<KeyT>(key[i], a.pass);
+      unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+      for (int bit = 0; bit < kRadixBits; ++bit) {
+        const bool set = ((d >> bit) & 1u) != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, set);
+        peers &= set ? m : ~m;
+      }
+      if (!valid) peers = 0;  // lanes past the end of the tile drop out
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (valid && lane == leader)
+        old = atomicAdd(&s_warp_cnt[warp][d], __popc(peers));
+      old = __shfl_sync(0xffffffffu, old, leader < 0 ? 0 : leader);
+      rank[i] = old + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // ---- per digit (thread tid owns digit tid): exclusive scan over warps,
+    //      tile total, publish, look-back over earlier tiles
+    uint32_t tile_count = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+      const uint32_t c = s_warp_cnt[w][tid];
+      s_warp_cnt[w][tid] = tile_count;
+      tile_count += c;
+    }
+    StVolatile(&lb[static_cast<size_t>(tile) * kRadix],
+               (tile == 0 ? kFlagPrefix : kFlagAgg) | tile_count);
+
+    // tile-local exclusive scan of the digit counts (block scan, 256 owners)
+    uint32_t tscan = tile_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, tscan, o);
+      if (lane >= o) tscan += t;
+    }
+    if (lane == 31) s_scan[warp] = tscan;
+
+    uint32_t exclusive = 0;
+    if (tile > 0 && a.debug != 1) {
+      int prev = tile - 1;
+      while (true) {
+        uint32_t s = LdVolatile(&lb[static_cast<size_t>(prev) * kRadix]);
+        while ((s & ~kValueMask) == 0)
+          s = LdVolatile(&lb[static_cast<size_t>(prev) * kRadix]);
+        exclusive += s & kValueMask;
+        if ((s & kFlagPrefix) != 0) break;
+        --prev;
+      }
+      StVolatile(&lb[static_cast<size_t>(tile) * kRadix],
+                 kFlagPrefix | (exclusive + tile_count));
+    }
+    __syncthreads();
+    uint32_t tbase = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w)
+      if (w < warp) tbase += s_scan[w];
+    const uint32_t t_excl = tbase + tscan - tile_count;
+    s_tile_excl[tid] = t_excl;
+    s_goff[tid] = static_cast<int32_t>(digit_base + exclusive) -
+                  static_cast<int32_t>(t_excl);
+    __syncthreads();
+
+    // ---- final position of every item inside the tile; keys through smem
+    uint32_t pos[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int local = warp_base + i * 32 + lane;
+      if (local < tile_n) {
+        const uint32_t d = DigitOf<KeyT>(key[i], a.pass);
+        pos[i] = s_tile_excl[d] + s_warp_cnt[warp][d] + rank[i];
+        s_exch[pos[i]] = key[i];
+      } else {
+        pos[i] = 0;
+      }
+    }
+    __syncthreads();
+    int32_t gaddr[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int p = tid + i * kCtaThreads;
+      if (p < tile_n) {
+        const KeyT k = s_exch[p];
+        gaddr[i] = s_goff[DigitOf<KeyT>(k, a.pass)] + p;
+        kout[gaddr[i]] = k;
+      } else {
+        gaddr[i] = -1;
+      }
+    }
+    __syncthreads();
+
+    // ---- payload: sample ids (same type as keys) through the same buffer
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int local = warp_base + i * 32 + lane;
+      if (local < tile_n) s_exch[pos[i]] = vin[tile_base + local];
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       const int p = tid + i * kCtaThreads;
-      if (p < tile_n) wout[gaddr[i]] = s_w[p];
+      if (p < tile_n) vout[gaddr[i]] = s_exch[p];
     }
+
+    // ---- payload: weights
+    if constexpr (WBYTES != 0) {
+      __syncthreads();
+      WT* s_w = reinterpret_cast<WT*>(s_exch_raw);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int local = warp_base + i * 32 + lane;
+        if (local < tile_n) s_w[pos[i]] = win[tile_base + local];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int p = tid + i * kCtaThreads;
+        if (p < tile_n) wout[gaddr[i]] = s_w[p];
+      }
+    }
+
   }
 }
 
@@ -468,26 +572,30 @@ struct SortLayout {
   int tile;
   int num_tiles;
   size_t hist_off, counters_off, lookback_off, zero_bytes;
-  size_t keys_tmp_off, vals_tmp_off, w_tmp_off, total;
+  size_t plan_off, keys_tmp_off, vals_tmp_off, w_tmp_off, total;
+  int tile_pitch;
 };
 
 SortLayout MakeSortLayout(int nnz, int idx_type, int wbytes) {
   SortLayout L;
   const int nd = static_cast<int>(IndexSize(idx_type));
   static const int items_env = EnvInt("CUEMBED_SORT_ITEMS", 0);
-  L.items = items_env > 0 ? items_env : (idx_type == CUEMBED_I64 ? 8 : 16);
+  L.items = items_env > 0 ? items_env : 8;
   if (L.items != 8 && L.items != 16) L.items = 8;
   L.tile = L.items * kCtaThreads;
   L.num_tiles = nnz > 0 ? (nnz + L.tile - 1) / L.tile : 0;
   size_t off = 0;
   L.hist_off = off;
   off += static_cast<size_t>(nd) * kRadix * sizeof(uint32_t);
-  L.counters_off = off;
-  off += AlignUp(static_cast<size_t>(nd) * sizeof(uint32_t), 128);
+  L.counters_off = off;  // nd tile counters + 1 "CTAs done" counter
+  off += AlignUp(static_cast<size_t>(nd + 1) * sizeof(uint32_t), 128);
   L.lookback_off = off;
-  off += static_cast<size_t>(nd) * L.num_tiles * kRadix * sizeof(uint32_t);
+  L.tile_pitch = L.num_tiles;
+  off += static_cast<size_t>(nd) * kRadix * L.tile_pitch * sizeof(uint32_t);
   L.zero_bytes = off;
   off = AlignUp(off, 256);
+  L.plan_off = off;
+  off += 256;
   L.keys_tmp_off = off;
   off += AlignUp(static_cast<size_t>(nnz) * nd, 256);
   L.vals_tmp_off = off;
@@ -503,16 +611,20 @@ void LaunchPasses(const SortArgs& base, cudaStream_t stream) {
   constexpr int ND = sizeof(KeyT);
   const size_t smem = static_cast<size_t>(ITEMS) * kCtaThreads * sizeof(KeyT);
   auto kernel = RadixPassKernel<KeyT, WBYTES, ITEMS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(smem));
-    attr_set = true;
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kCtaThreads, smem);
+    ctas_per_sm = n > 0 ? n : 1;
   }
+  const int cap = GetDeviceInfo().sm_count * ctas_per_sm;
+  const int grid = base.num_tiles < cap ? base.num_tiles : cap;
   for (int p = 0; p < ND; ++p) {
     SortArgs a = base;
     a.pass = p;
-    kernel<<<a.num_tiles, kCtaThreads, smem, stream>>>(a);
+    kernel<<<grid, kCtaThreads, smem, stream>>>(a);
   }
   CountLaunch(ND);
 }
@@ -526,14 +638,14 @@ void LaunchPassesItems(const SortArgs& a, int items, cudaStream_t stream) {
 }
 
 template <typename KeyT>
-void LaunchSortTyped(const SortArgs& a, int wbytes, int items,
-                     cudaStream_t stream) {
+void LaunchSortTyped(const SortArgs& a, uint32_t* hist, int* plan, int wbytes,
+                     int items, cudaStream_t stream) {
   {
-    const int ctas = CeilDiv(a.nnz, kCtaThreads * 8);
+    const int ctas = CeilDiv(a.nnz, kCtaThreads * 16);
     const int cap = GetDeviceInfo().sm_count * 4;
     RadixHistKernel<KeyT><<<ctas < cap ? ctas : cap, kCtaThreads, 0, stream>>>(
-        static_cast<const KeyT*>(a.keys_in), a.nnz,
-        const_cast<uint32_t*>(a.hist));
+        static_cast<const KeyT*>(a.keys_in), a.nnz, hist,
+        a.tile_counters + sizeof(KeyT), plan);
     CountLaunch();
   }
   if (wbytes == 0)
@@ -587,126 +699,171 @@ int LaunchTranspose(const void* rows, const void* cols, const void* weights,
   a.keys_tmp = work + L.keys_tmp_off;
   a.vals_tmp = work + L.vals_tmp_off;
   a.w_tmp = work + L.w_tmp_off;
-  a.hist = reinterpret_cast<const uint32_t*>(work + L.hist_off);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(work + L.hist_off);
+  int* plan = reinterpret_cast<int*>(work + L.plan_off);
+  a.digit_base = hist;
+  a.plan = plan;
   a.lookback = reinterpret_cast<uint32_t*>(work + L.lookback_off);
   a.tile_counters = reinterpret_cast<uint32_t*>(work + L.counters_off);
   a.nnz = nnz;
   a.num_tiles = L.num_tiles;
+  a.tile_pitch = L.tile_pitch;
+  static const int debug_env = EnvInt("CUEMBED_SORT_DEBUG", 0);
+  a.debug = debug_env;
   a.pass = 0;
   if (idx_type == CUEMBED_I64)
-    LaunchSortTyped<int64_t>(a, wbytes, L.items, stream);
+    LaunchSortTyped<int64_t>(a, hist, plan, wbytes, L.items, stream);
   else
-    LaunchSortTyped<int32_t>(a, wbytes, L.items, stream);
+    LaunchSortTyped<int32_t>(a, hist, plan, wbytes, L.items, stream);
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
 
 // ------------------------------------------- compressed gradient indices
 
-// remapped[i] = number of positions j in (0, i] with idx[j] != idx[j-1]:
-// single pass, decoupled look-back over tile totals.
-// status word: 2 flag bits + 62 value bits.
-constexpr unsigned long long kFlagAgg64 = 1ull << 62;
-constexpr unsigned long long kFlagPrefix64 = 2ull << 62;
-constexpr unsigned long long kValueMask64 = (1ull << 62) - 1ull;
+// remapped[i] = number of positions j in (0, i] with idx[j] != idx[j-1].
+// Two kernels over the same fixed partition of the array into `parts` ranges:
+//   1. count the run starts of every range;
+//   2. every CTA sums the counts of the ranges before its own (<= 2048 values,
+//      one block reduction) and then scans its range.
+// No cross-CTA waiting (a single-pass look-back scan was measured latency-bound
+// at this size: 36 us for 4 M indices, profiles/r01_notes.md); the second read
+// of the indices comes from L2.
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanItems * kCtaThreads;  // 2048
+constexpr int kScanMaxParts = 2048;
 
-__device__ __forceinline__ unsigned long long LdVolatile64(
-    const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void StVolatile64(unsigned long long* p,
-                                             unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+// Thread-blocked: kScanItems consecutive elements starting at `base` (a
+// multiple of kScanItems), fetched with 16-byte loads; the element before the
+// thread's range comes from the neighbouring lane.
+template <typename IdxT>
+__device__ __forceinline__ uint32_t LoadFlags(const IdxT* __restrict__ idx,
+                                              int64_t base, int64_t nnz,
+                                              bool vec_ok, uint32_t* flag) {
+  constexpr int PER = 16 / sizeof(IdxT);
+  IdxT cur[kScanItems];
+  if (vec_ok && base + kScanItems <= nnz) {
+#pragma unroll
+    for (int k = 0; k < kScanItems / PER; ++k) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(idx + base) + k);
+      *reinterpret_cast<uint4*>(&cur[k * PER]) = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+      cur[i] = base + i < nnz ? __ldg(idx + base + i) : IdxT(0);
+  }
+  // last element of the previous thread's range
+  IdxT prev;
+  if constexpr (sizeof(IdxT) == 8)
+    prev = static_cast<IdxT>(__shfl_up_sync(
+        0xffffffffu, static_cast<long long>(cur[kScanItems - 1]), 1));
+  else
+    prev = __shfl_up_sync(0xffffffffu, cur[kScanItems - 1], 1);
+  if ((threadIdx.x & 31) == 0)
+    prev = (base > 0 && base - 1 < nnz) ? __ldg(idx + base - 1) : IdxT(0);
+  uint32_t local = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const int64_t g = base + i;
+    flag[i] = (g > 0 && g < nnz && cur[i] != prev) ? 1u : 0u;
+    local += flag[i];
+    prev = cur[i];
+  }
+  return local;
 }
 
-template <typename IdxT, int ITEMS>
+template <typename IdxT>
 __global__ void __launch_bounds__(kCtaThreads)
-    CompressIndicesKernel(const IdxT* __restrict__ idx, int nnz,
-                          IdxT* __restrict__ remapped,
-                          unsigned long long* __restrict__ status,
-                          uint32_t* __restrict__ tile_counter) {
-  constexpr int TILE = ITEMS * kCtaThreads;
-  __shared__ int s_tile;
+    CompressCountKernel(const IdxT* __restrict__ idx, int nnz, int chunks_per_part,
+                        bool vec_ok, uint32_t* __restrict__ part_counts) {
   __shared__ uint32_t s_warp[kWarpsPerCta];
-  __shared__ unsigned long long s_excl;
+  const int tid = threadIdx.x;
+  const int64_t part_begin =
+      static_cast<int64_t>(blockIdx.x) * chunks_per_part * kScanChunk;
+  uint32_t local = 0;
+  for (int c = 0; c < chunks_per_part; ++c) {
+    const int64_t chunk_begin = part_begin + static_cast<int64_t>(c) * kScanChunk;
+    if (chunk_begin >= nnz) break;  // uniform for the CTA
+    const int64_t base = chunk_begin + tid * kScanItems;
+    uint32_t flag[kScanItems];
+    local += LoadFlags<IdxT>(idx, base, nnz, vec_ok, flag);
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((tid & 31) == 0) s_warp[tid >> 5] = local;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) total += s_warp[w];
+    part_counts[blockIdx.x] = total;
+  }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kCtaThreads)
+    CompressScanKernel(const IdxT* __restrict__ idx, int nnz, int chunks_per_part,
+                       bool vec_ok, const uint32_t* __restrict__ part_counts,
+                       IdxT* __restrict__ remapped) {
+  __shared__ unsigned long long s_red[kWarpsPerCta];
+  __shared__ uint32_t s_warp[kWarpsPerCta];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  if (tid == 0) s_tile = static_cast<int>(atomicAdd(tile_counter, 1u));
+  // run starts in all earlier parts
+  unsigned long long before = 0;
+  for (int p = tid; p < static_cast<int>(blockIdx.x); p += kCtaThreads)
+    before += part_counts[p];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) s_red[warp] = before;
   __syncthreads();
-  const int tile = s_tile;
-  const int64_t base = static_cast<int64_t>(tile) * TILE + tid * ITEMS;
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int w = 0; w < kWarpsPerCta; ++w) carry += s_red[w];
 
-  // Blocked layout: thread owns ITEMS consecutive elements.
-  uint32_t flag[ITEMS];
-  uint32_t local = 0;
-  IdxT prev = (base > 0 && base - 1 < nnz) ? __ldg(idx + base - 1) : IdxT(0);
+  const int64_t part_begin =
+      static_cast<int64_t>(blockIdx.x) * chunks_per_part * kScanChunk;
+  for (int c = 0; c < chunks_per_part; ++c) {
+    const int64_t base = part_begin + static_cast<int64_t>(c) * kScanChunk +
+                         tid * kScanItems;
+    if (part_begin + static_cast<int64_t>(c) * kScanChunk >= nnz) break;
+    uint32_t flag[kScanItems];
+    const uint32_t local = LoadFlags<IdxT>(idx, base, nnz, vec_ok, flag);
+    uint32_t scan = local;
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int64_t g = base + i;
-    IdxT cur = g < nnz ? __ldg(idx + g) : prev;
-    flag[i] = (g > 0 && g < nnz && cur != prev) ? 1u : 0u;
-    local += flag[i];
-    prev = cur;
-  }
-  // block exclusive scan of `local`
-  uint32_t scan = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
-    if (lane >= o) scan += t;
-  }
-  if (lane == 31) s_warp[warp] = scan;
-  __syncthreads();
-  uint32_t wbase = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kWarpsPerCta; ++w) {
-    if (w < warp) wbase += s_warp[w];
-    total += s_warp[w];
-  }
-  const uint32_t thread_excl = wbase + scan - local;
-
-  // Warp 0 resolves the totals of all earlier tiles, 32 predecessors per step.
-  if (warp == 0) {
-    unsigned long long exclusive = 0;
-    if (tile == 0) {
-      if (lane == 0) StVolatile64(&status[0], kFlagPrefix64 | total);
-    } else {
-      if (lane == 0) StVolatile64(&status[tile], kFlagAgg64 | total);
-      int p = tile - 1;
-      while (true) {
-        const int q = p - lane;
-        unsigned long long s = kFlagPrefix64;  // before tile 0: prefix 0
-        if (q >= 0) {
-          do {
-            s = LdVolatile64(&status[q]);
-          } while ((s & ~kValueMask64) == 0);
-        }
-        const unsigned pm =
-            __ballot_sync(0xffffffffu, (s & kFlagPrefix64) != 0);
-        const int first = __ffs(pm) - 1;  // nearest predecessor with a prefix
-        unsigned long long v =
-            (pm == 0 || lane <= first) ? (s & kValueMask64) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-          v += __shfl_xor_sync(0xffffffffu, v, o);
-        exclusive += v;
-        if (pm != 0) break;
-        p -= 32;
-      }
-      if (lane == 0)
-        StVolatile64(&status[tile], kFlagPrefix64 | (exclusive + total));
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+      if (lane >= o) scan += t;
     }
-    if (lane == 0) s_excl = exclusive;
-  }
-  __syncthreads();
-  unsigned long long running = s_excl + thread_excl;
+    __syncthreads();  // s_warp reuse
+    if (lane == 31) s_warp[warp] = scan;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int64_t g = base + i;
-    running += flag[i];
-    if (g < nnz) remapped[g] = static_cast<IdxT>(running);
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+      if (w < warp) wbase += s_warp[w];
+      total += s_warp[w];
+    }
+    unsigned long long running = carry + wbase + scan - local;
+    IdxT outv[kScanItems];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      running += flag[i];
+      outv[i] = static_cast<IdxT>(running);
+    }
+    if (vec_ok && base + kScanItems <= nnz) {
+      constexpr int PER = 16 / sizeof(IdxT);
+#pragma unroll
+      for (int k = 0; k < kScanItems / PER; ++k)
+        reinterpret_cast<uint4*>(remapped + base)[k] =
+            *reinterpret_cast<uint4*>(&outv[k * PER]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kScanItems; ++i)
+        if (base + i < nnz) remapped[base + i] = outv[i];
+    }
+    carry += total;
   }
 }
 
@@ -715,10 +872,12 @@ int LaunchCompressedGradIndices(const void* indices, int idx_type, int nnz,
                                 cudaStream_t stream) {
   if (lwork == nullptr || nnz < 0) return CUEMBED_ERR_ARGUMENT;
   if (idx_type < 0 || idx_type > 1) return CUEMBED_ERR_DTYPE;
-  constexpr int ITEMS = 8;
-  constexpr int TILE = ITEMS * kCtaThreads;
-  const int num_tiles = nnz > 0 ? (nnz + TILE - 1) / TILE : 0;
-  const size_t need = 128 + static_cast<size_t>(num_tiles) * 8;
+  const int num_chunks = nnz > 0 ? (nnz + kScanChunk - 1) / kScanChunk : 0;
+  const int chunks_per_part =
+      num_chunks > 0 ? (num_chunks + kScanMaxParts - 1) / kScanMaxParts : 1;
+  const int parts =
+      num_chunks > 0 ? (num_chunks + chunks_per_part - 1) / chunks_per_part : 0;
+  const size_t need = 256 + static_cast<size_t>(parts) * sizeof(uint32_t);
   if (work == nullptr) {
     *lwork = need;
     return CUEMBED_OK;
@@ -726,23 +885,25 @@ int LaunchCompressedGradIndices(const void* indices, int idx_type, int nnz,
   if (*lwork < need) return CUEMBED_ERR_WORKSPACE;
   if (nnz == 0) return CUEMBED_OK;
   if (indices == nullptr || remapped == nullptr) return CUEMBED_ERR_ARGUMENT;
-  if ((reinterpret_cast<uintptr_t>(work) & 7) != 0) return CUEMBED_ERR_ARGUMENT;
-  if (cudaMemsetAsync(work, 0, need, stream) != cudaSuccess)
-    return CUEMBED_ERR_CUDA;
-  uint32_t* counter = reinterpret_cast<uint32_t*>(work);
-  unsigned long long* status =
-      reinterpret_cast<unsigned long long*>(work + 128);
-  if (idx_type == CUEMBED_I64)
-    CompressIndicesKernel<int64_t, ITEMS>
-        <<<num_tiles, kCtaThreads, 0, stream>>>(
-            static_cast<const int64_t*>(indices), nnz,
-            static_cast<int64_t*>(remapped), status, counter);
-  else
-    CompressIndicesKernel<int32_t, ITEMS>
-        <<<num_tiles, kCtaThreads, 0, stream>>>(
-            static_cast<const int32_t*>(indices), nnz,
-            static_cast<int32_t*>(remapped), status, counter);
-  CountLaunch();
+  if ((reinterpret_cast<uintptr_t>(work) & 3) != 0) return CUEMBED_ERR_ARGUMENT;
+  // 16-byte vector loads / stores only when both arrays allow them.
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(indices) |
+                        reinterpret_cast<uintptr_t>(remapped)) & 15) == 0;
+  uint32_t* counts = reinterpret_cast<uint32_t*>(work);
+  if (idx_type == CUEMBED_I64) {
+    CompressCountKernel<int64_t><<<parts, kCtaThreads, 0, stream>>>(
+        static_cast<const int64_t*>(indices), nnz, chunks_per_part, vec_ok, counts);
+    CompressScanKernel<int64_t><<<parts, kCtaThreads, 0, stream>>>(
+        static_cast<const int64_t*>(indices), nnz, chunks_per_part, vec_ok, counts,
+        static_cast<int64_t*>(remapped));
+  } else {
+    CompressCountKernel<int32_t><<<parts, kCtaThreads, 0, stream>>>(
+        static_cast<const int32_t*>(indices), nnz, chunks_per_part, vec_ok, counts);
+    CompressScanKernel<int32_t><<<parts, kCtaThreads, 0, stream>>>(
+        static_cast<const int32_t*>(indices), nnz, chunks_per_part, vec_ok, counts,
+        static_cast<int32_t*>(remapped));
+  }
+  CountLaunch(2);
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
 

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out/prof_*.ncu-rep into profiles/<tag>_ncu_summary.json
+(and print a markdown table).  Usage: python scripts/ncu_summary.py r01"""
+import csv, glob, json, os, subprocess, sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANT = {
+    "gpu__time_duration.sum": "duration_us",
+    "dram__bytes_read.sum": "dram_read",
+    "dram__bytes_write.sum": "dram_write",
+    "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
+    "launch__registers_per_thread": "registers",
+    "sm__inst_executed.avg.per_cycle_active": "ipc",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1_throughput_pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "ld_sectors",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum": "ld_requests",
+}
+SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+out = {}
+for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", "prof_*.ncu-rep"))):
+    name = os.path.basename(rep)[5:-8]
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, unit, vals = rows[0], rows[1], rows[2]
+    d = {"kernel": vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else name}
+    for i, h in enumerate(hdr):
+        if h in WANT:
+            try:
+                v = float(vals[i])
+            except ValueError:
+                continue
+            v *= SCALE.get(unit[i], 1.0)
+            d[WANT[h]] = v
+    if "dram_read" in d and "dram_write" in d:
+        d["dram_bytes"] = d["dram_read"] + d["dram_write"]
+    if d.get("ld_requests"):
+        d["sectors_per_request"] = d["ld_sectors"] / d["ld_requests"]
+    out[name] = d
+os.makedirs(os.path.join(root, "profiles"), exist_ok=True)
+path = os.path.join(root, "profiles", f"{tag}_ncu_summary.json")
+json.dump(out, open(path, "w"), indent=1)
+print("| kernel | dur us | DRAM MB (r+w) | L2 hit % | L1 hit % | occ % | regs | IPC | issue % | L2 tput % | DRAM tput % | sect/req |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+for k, d in out.items():
+    print(f"| {k} | {d.get('duration_us',0):.1f} | {d.get('dram_bytes',0)/1e6:.1f} | {d.get('l2_hit_pct',0):.1f} | "
+          f"{d.get('l1_hit_pct',0):.1f} | {d.get('achieved_occupancy_pct',0):.1f} | {int(d.get('registers',0))} | "
+          f"{d.get('ipc',0):.2f} | {d.get('issue_active_pct',0):.1f} | {d.get('l2_throughput_pct',0):.1f} | "
+          f"{d.get('dram_throughput_pct',0):.1f} | {d.get('sectors_per_request',0):.1f} |")
+print("wrote", path)
