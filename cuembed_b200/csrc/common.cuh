@@ -35,9 +35,17 @@ inline const DeviceInfo& GetDeviceInfo() {
   if (dev < 0 || dev >= 64) dev = 0;
   if (!ready[dev]) {
     DeviceInfo d;
+    d.sm_count = 0;
+    d.max_smem_optin = 0;
     cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&d.max_smem_optin,
                            cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // Workspace queries must also work where no device is visible (build
+    // hosts): size them for the part this library is written for.
+    if (d.sm_count <= 0) {
+      d.sm_count = 148;
+      cudaGetLastError();
+    }
     info[dev] = d;
     ready[dev] = true;
   }

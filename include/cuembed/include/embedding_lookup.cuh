@@ -1,0 +1,94 @@
+// Drop-in replacement for cuembed/include/embedding_lookup.cuh
+// (NVIDIA/cuEmbed @ 90dd8436): the same host templates in namespace cuembed,
+// forwarding to the B200-native kernels in libcuembed_b200.so through the C
+// ABI of include/cuembed_b200.h.  Callers keep
+//     #include "cuembed/include/embedding_lookup.cuh"
+// put <repo>/include on the include path and link -lcuembed_b200.
+//
+//   EmbeddingForward   replaces cuembed/include/embedding_lookup.cuh:245-308
+//   EmbeddingBackward  replaces cuembed/include/embedding_lookup.cuh:423-483
+// Misuse aborts with a "Check failed" message like CUEMBED_ASSERT (:151-158).
+#ifndef CUEMBED_INCLUDE_EMBEDDING_LOOKUP_CUH_
+#define CUEMBED_INCLUDE_EMBEDDING_LOOKUP_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <iostream>
+
+#include "cuembed/include/embedding_lookup_types.cuh"
+#include "cuembed_b200.h"
+
+namespace cuembed {
+
+#define CUEMBED_ASSERT(condition)                                           \
+  do {                                                                      \
+    if (!(condition)) {                                                     \
+      std::cerr << "Check failed: " #condition << " at " << __FILE__ << ":" \
+                << __LINE__ << std::endl;                                   \
+      std::abort();                                                         \
+    }                                                                       \
+  } while (0)
+
+namespace b200_detail {
+// A non-zero C-ABI code is a violated precondition: abort like the reference.
+inline void CheckCode(int code, const char* what) {
+  if (code != CUEMBED_OK) {
+    std::cerr << what << ": " << cuembed_error_string(code) << std::endl;
+    std::abort();
+  }
+}
+inline int ModeCode(CombineMode mode) {
+  return mode == CombineMode::kSum
+             ? CUEMBED_SUM
+             : (mode == CombineMode::kMean ? CUEMBED_MEAN : CUEMBED_CONCAT);
+}
+}  // namespace b200_detail
+
+// Pooled embedding lookup, fixed hotness or CSR.  Template parameters and
+// arguments as in the reference; bf16 tables are additionally supported.
+template <typename InputT, typename OutputT, typename IndexT, typename OffsetT,
+          bool fp16_math = false>
+void EmbeddingForward(const InputT* params, const int embed_width,
+                      const IndexT* indices, const OffsetT* offsets,
+                      const GetElemT<InputT>* weights, const int batch_size,
+                      const int num_hots, const CombineMode mode, OutputT* ret,
+                      const cudaStream_t stream = 0) {
+  using ElemT = GetElemT<InputT>;
+  b200_detail::CheckCode(
+      cuembed_forward(params, b200_detail::DTypeCode<ElemT>::value, embed_width,
+                      indices, b200_detail::ITypeCode<IndexT>::value, offsets,
+                      b200_detail::ITypeCode<OffsetT>::value, weights,
+                      batch_size, num_hots, b200_detail::ModeCode(mode),
+                      fp16_math ? 1 : 0, ret,
+                      b200_detail::DTypeCode<GetElemT<OutputT>>::value,
+                      reinterpret_cast<cuembed_stream_t>(stream)),
+      "EmbeddingForward");
+}
+
+// Gradient w.r.t. the table from the transposed COO indices; full or
+// compressed.  Deterministic (fixed summation order, no atomics).
+template <typename GradT, typename IndexT>
+void EmbeddingBackward(const GradT* grad_y, const int embed_width,
+                       const int num_grad_embedding_rows, const int nnz,
+                       const IndexT* transpose_indices,
+                       const IndexT* transpose_sample_ids,
+                       const IndexT* transpose_remapped_indices,
+                       const GradT* transpose_weights,
+                       const bool skip_grad_init, GradT* grad_embedding,
+                       IndexT* inverse_mapping,
+                       const cudaStream_t stream = 0) {
+  b200_detail::CheckCode(
+      cuembed_backward(grad_y, b200_detail::DTypeCode<GradT>::value,
+                       embed_width, num_grad_embedding_rows, nnz,
+                       b200_detail::ITypeCode<IndexT>::value,
+                       transpose_indices, transpose_sample_ids,
+                       transpose_remapped_indices, transpose_weights,
+                       skip_grad_init ? 1 : 0, grad_embedding, inverse_mapping,
+                       reinterpret_cast<cuembed_stream_t>(stream)),
+      "EmbeddingBackward");
+}
+
+}  // namespace cuembed
+
+#endif  // CUEMBED_INCLUDE_EMBEDDING_LOOKUP_CUH_
