@@ -9,12 +9,13 @@ loads (and if necessary builds) the library and fails loudly if it cannot.
 """
 from .api import (CombineMode, ComputeCompressedGradIndices, CuEmbedError,
                   EmbeddingBackward, EmbeddingForward, ExtractRowIdsForConcat,
-                  ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, Transpose,
-                  backward_workspace_bytes, launch_count)
+                  ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, ShardFinalize,
+                  ShardSelect, Transpose, backward_workspace_bytes,
+                  launch_count)
 
 __all__ = [
     "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward",
     "ExtractRowIdsFromFixed", "ExtractRowIdsFromCSR", "ExtractRowIdsForConcat",
     "Transpose", "ComputeCompressedGradIndices", "backward_workspace_bytes",
-    "launch_count",
+    "launch_count", "ShardSelect", "ShardFinalize",
 ]

@@ -31,6 +31,11 @@ SIGNATURES = {
                                _ci, _vp, _vp, _vp]),
     "cuembed_backward_ws": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp,
                                   _vp, _ci, _vp, _vp, _vp, _szp, _vp]),
+    "cuembed_shard_select": (_ci, [_vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
+                                   ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
+                                   _vp, _vp, _szp, _vp]),
+    "cuembed_shard_finalize": (_ci, [_vp, _ci, _ci, _ci, _vp, _ci, _ci, _ci, _vp,
+                                     _ci, _vp, _ci, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }
 

@@ -213,3 +213,49 @@ def backward_workspace_bytes(dtype: torch.dtype, embed_width: int, nnz: int,
         None, _DT[dtype], int(embed_width), 0, int(nnz), _IT[index_dtype], None,
         None, None, None, 1, None, None, None, ctypes.byref(lwork), None))
     return int(lwork.value)
+
+
+# ---------------------------------------------------------------- sharded mode
+def ShardSelect(indices: torch.Tensor, offsets: Optional[torch.Tensor],
+                weights: Optional[torch.Tensor], batch_size: int, num_hots: int,
+                row_lo: int, row_hi: int, local_offsets: Optional[torch.Tensor],
+                local_indices: Optional[torch.Tensor],
+                local_weights: Optional[torch.Tensor],
+                work: Optional[torch.Tensor], stream=None) -> int:
+    """cuembed_shard_select: compact local CSR of the lookups in
+    [row_lo, row_hi).  work=None is the workspace query (returns bytes)."""
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(0 if work is None else work.numel())
+    wdt = _dt(weights) if weights is not None else 0
+    if work is None:
+        _check(lib.cuembed_shard_select(
+            None, _it(indices), ctypes.c_void_p(1) if offsets is not None else None,
+            _it(offsets) if offsets is not None else 0, None, wdt, int(batch_size),
+            int(num_hots), int(row_lo), int(row_hi), None, None, None, None,
+            ctypes.byref(lwork), _stream(stream)))
+        return int(lwork.value)
+    if local_offsets.dtype != torch.int32:
+        raise CuEmbedError("local_offsets must be int32")
+    _check(lib.cuembed_shard_select(
+        _dev(indices, "indices"), _it(indices), _dev(offsets, "offsets"),
+        _it(offsets) if offsets is not None else 0, _dev(weights, "weights"), wdt,
+        int(batch_size), int(num_hots), int(row_lo), int(row_hi),
+        _dev(local_offsets, "local_offsets"), _dev(local_indices, "local_indices"),
+        _dev(local_weights, "local_weights"), _dev(work, "work"),
+        ctypes.byref(lwork), _stream(stream)))
+    return int(lwork.value)
+
+
+def ShardFinalize(partial: torch.Tensor, n_samples: int, embed_width: int,
+                  mode: CombineMode, offsets: Optional[torch.Tensor],
+                  num_hots: int, sample0: int, weights: Optional[torch.Tensor],
+                  out: torch.Tensor, stream=None) -> None:
+    """cuembed_shard_finalize: epilogue after the reduce-scatter."""
+    if partial.dtype != torch.float32:
+        raise CuEmbedError("partial sums must be float32")
+    _check(_lib.load().cuembed_shard_finalize(
+        _dev(partial, "partial"), int(n_samples), int(embed_width), int(mode),
+        _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+        int(num_hots), int(sample0), _dev(weights, "weights"),
+        _dt(weights) if weights is not None else 0, _dev(out, "out"), _dt(out),
+        _stream(stream)))

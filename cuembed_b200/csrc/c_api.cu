@@ -171,6 +171,29 @@ int cuembed_backward(const void* grad_y, int dtype, int embed_width,
   return rc;
 }
 
+int cuembed_shard_select(const void* indices, int idx_type, const void* offsets,
+                         int off_type, const void* weights, int weight_dtype,
+                         int batch_size, int num_hots, long long row_lo,
+                         long long row_hi, int* local_offsets,
+                         void* local_indices, void* local_weights, char* work,
+                         size_t* lwork, cuembed_stream_t stream) {
+  return LaunchShardSelect(indices, idx_type, offsets, off_type, weights,
+                           weight_dtype, batch_size, num_hots, row_lo, row_hi,
+                           local_offsets, local_indices, local_weights, work,
+                           lwork, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_shard_finalize(const void* partial_f32, int n_samples,
+                           int embed_width, int mode, const void* offsets,
+                           int off_type, int num_hots, int sample0,
+                           const void* weights, int weight_dtype, void* out,
+                           int out_dtype, cuembed_stream_t stream) {
+  return LaunchShardFinalize(partial_f32, n_samples, embed_width, mode, offsets,
+                             off_type, num_hots, sample0, weights, weight_dtype,
+                             out, out_dtype,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
 unsigned long long cuembed_launch_count(void) { return g_launches.load(); }
 
 }  // extern "C"

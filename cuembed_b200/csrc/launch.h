@@ -45,6 +45,19 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
                    void* grad_embedding, void* inverse_mapping, char* work,
                    size_t* lwork, cudaStream_t stream);
 
+int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
+                      int off_type, const void* weights, int weight_dtype,
+                      int batch_size, int num_hots, long long row_lo,
+                      long long row_hi, int* local_offsets,
+                      void* local_indices, void* local_weights, char* work,
+                      size_t* lwork, cudaStream_t stream);
+
+int LaunchShardFinalize(const void* partial_f32, int n_samples, int embed_width,
+                        int mode, const void* offsets, int off_type,
+                        int num_hots, int sample0, const void* weights,
+                        int weight_dtype, void* out, int out_dtype,
+                        cudaStream_t stream);
+
 }  // namespace cuembed_b200
 
 #endif  // CUEMBED_B200_CSRC_LAUNCH_H_

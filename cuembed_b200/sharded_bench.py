@@ -1,0 +1,269 @@
+"""bench.py --gpus N (N > 1): the row-sharded path, one process per GPU.
+
+Weak scaling of the headline workload: every rank owns a C2-sized shard
+(10 M x 256 fp16 rows), the global table has N x 10 M rows, the global batch
+N x 65536 bags of hotness 64 drawn from the power law over the GLOBAL table
+(replicated on every rank).  One step =
+    forward : shard select -> local pool (fp32 partial) -> NCCL reduce-scatter
+              -> epilogue
+    transpose: row ids + sort + compressed remap of the rank's own lookups
+    backward: NCCL all-gather of grad_y -> local backward (compressed)
+Stage times are CUDA-event times, max over ranks, L2 flushed before every
+stage.  value = global lookups / step time.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def power_law_torch(gen, n, num_categories, alpha, device):
+    u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
+    if alpha == 0.0:
+        y = u * num_categories + 1.0
+    else:
+        g = 1.0 - alpha
+        hi = float(num_categories + 1) ** g
+        y = (u * (hi - 1.0) + 1.0) ** (1.0 / g)
+    return y.floor().clamp_(1, num_categories).to(torch.int64)
+
+
+def unique_bags_torch(gen, batch, hot, num_categories, alpha, device):
+    """GPU version of cuembed_b200.datagen.unique_bags (same distribution)."""
+    n_cat = num_categories - 1
+    bags = power_law_torch(gen, batch * hot, n_cat, alpha, device).view(batch, hot)
+    while True:
+        bags, _ = torch.sort(bags, dim=1)
+        dup = torch.zeros_like(bags, dtype=torch.bool)
+        dup[:, 1:] = bags[:, 1:] == bags[:, :-1]
+        n_dup = int(dup.sum().item())
+        if n_dup == 0:
+            break
+        bags[dup] = power_law_torch(gen, n_dup, n_cat, alpha, device)
+    perm = torch.randperm(n_cat + 1, generator=gen, device=device)
+    bags = perm[bags]
+    keys = torch.rand(bags.shape, generator=gen, device=device)
+    order = torch.argsort(keys, dim=1)
+    return torch.gather(bags, 1, order)
+
+
+def run(args, rank, local_rank, world):
+    import bench
+    import cuembed_b200 as ce
+    from cuembed_b200.sharded import RowShardedEmbedding, row_range
+
+    dev = torch.device("cuda", local_rank)
+    cfg = dict(bench.WORKLOADS[args.workload])
+    tdt = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[cfg["dtype"]]
+    idt = torch.int32 if cfg["index"] == "int32" else torch.int64
+    shard_rows, w, hot = cfg["num_categories"], cfg["embed_width"], cfg["hotness"]
+    rows = shard_rows * world
+    batch = cfg["batch_size"] * world
+    nnz = batch * hot
+    lo, hi = row_range(rows, world, rank)
+
+    # replicated indices: rank 0 generates, everyone receives
+    indices = torch.empty(nnz, dtype=idt, device=dev)
+    if rank == 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234)
+        indices.copy_(unique_bags_torch(g, batch, hot, rows, cfg["alpha"], dev).view(-1).to(idt))
+    dist.broadcast(indices, src=0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(123456 + rank)
+    table = torch.empty(hi - lo, w, dtype=tdt, device=dev)
+    for r0 in range(0, hi - lo, 1 << 20):
+        r1 = min(hi - lo, r0 + (1 << 20))
+        table[r0:r1] = (torch.rand(r1 - r0, w, generator=g, device=dev) * 2 - 1).to(tdt)
+    per = batch // world
+    g.manual_seed(654321 + rank)
+    grad_slice = torch.randint(-10, 11, (per, w), generator=g, device=dev).to(tdt)
+
+    emb = RowShardedEmbedding(table, rows)
+    ops = emb.ops
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    state = {}
+
+    def forward():
+        out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+        state["out"], state["ctx"] = out, ctx
+
+    forward()
+    ctx = state["ctx"]
+    local_nnz = int(ctx.local_offsets[-1].item())
+    row_ids = torch.empty(local_nnz, dtype=idt, device=dev)
+    t_idx = torch.empty(local_nnz, dtype=idt, device=dev)
+    t_sid = torch.empty(local_nnz, dtype=idt, device=dev)
+    remapped = torch.empty(local_nnz, dtype=idt, device=dev)
+    l_idx = ctx.local_indices[:local_nnz]
+    lwork = max(ce.Transpose(row_ids, l_idx, None, local_nnz, None, None, None, None),
+                ce.ComputeCompressedGradIndices(l_idx, local_nnz, None, None))
+    work = torch.empty(lwork, dtype=torch.uint8, device=dev)
+
+    def transpose():
+        ce.ExtractRowIdsFromCSR(state["ctx"].local_offsets, batch, row_ids)
+        ce.Transpose(row_ids, l_idx, None, local_nnz, t_idx, t_sid, None, work)
+        ce.ComputeCompressedGradIndices(t_idx, local_nnz, remapped, work)
+
+    transpose()
+    num_unique = int(remapped[-1].item()) + 1
+    grad = torch.zeros(num_unique, w, dtype=tdt, device=dev)
+    inv = torch.empty(num_unique, dtype=idt, device=dev)
+    bwork = torch.empty(ce.backward_workspace_bytes(tdt, w, local_nnz, idt),
+                        dtype=torch.uint8, device=dev)
+    full_gy = torch.empty(batch, w, dtype=tdt, device=dev)
+
+    def backward():
+        dist.all_gather_into_tensor(full_gy, grad_slice)
+        ce.EmbeddingBackward(full_gy, w, num_unique, local_nnz, t_idx, t_sid, remapped,
+                             None, True, grad, inv, work=bwork)
+
+    stages = [("forward", forward), ("transpose", transpose), ("backward", backward)]
+    stream = torch.cuda.current_stream()
+
+    def one_step(times=None):
+        for name, fn in stages:
+            flush.fill_(1)
+            dist.barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            if times is not None:
+                times.append((name, e0, e1))
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ce.launch_count()
+    events = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(events)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    launches = ce.launch_count() - launches0
+    per_stage = {"forward": 0.0, "transpose": 0.0, "backward": 0.0}
+    for name, e0, e1 in events:
+        per_stage[name] += e0.elapsed_time(e1)
+    t = torch.tensor([per_stage[k] / args.steps for k in ("forward", "transpose", "backward")],
+                     dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, per stage
+    fwd_ms, tr_ms, bwd_ms = (float(x) for x in t.tolist())
+    ms_per_step = fwd_ms + tr_ms + bwd_ms
+
+    # communication alone (same buffers), for the report
+    partial = torch.empty(batch, w, dtype=torch.float32, device=dev)
+    mine = torch.empty(per, w, dtype=torch.float32, device=dev)
+    comm = {}
+    for name, fn in (("reduce_scatter", lambda: dist.reduce_scatter_tensor(mine, partial)),
+                     ("all_gather", lambda: dist.all_gather_into_tensor(full_gy, grad_slice))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        c = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        comm[name] = float(c.item())
+
+    # end to end with host buffers: indices in, output slice + gradient out
+    e2e_ms = float("nan")
+    h2d = d2h = 0
+    if not args.no_e2e:
+        idx_host = indices.cpu().pin_memory()
+        gy_host = grad_slice.cpu().pin_memory()
+        out_host = torch.empty(per, w, dtype=tdt).pin_memory()
+        grad_host = torch.empty(num_unique, w, dtype=tdt).pin_memory()
+        inv_host = torch.empty(num_unique, dtype=idt).pin_memory()
+
+        def e2e_step():
+            indices.copy_(idx_host, non_blocking=True)
+            forward()
+            out_host.copy_(state["out"], non_blocking=True)
+            grad_slice.copy_(gy_host, non_blocking=True)
+            transpose()
+            backward()
+            grad_host.copy_(grad, non_blocking=True)
+            inv_host.copy_(inv, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        c = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        e2e_ms = float(c.item())
+        es = table.element_size()
+        h2d = world * (nnz * indices.element_size() + per * w * es)
+        d2h = world * (per * w * es + num_unique * (w * es + indices.element_size()))
+
+    clocks = sampler.stop() if rank == 0 else None
+    peak, peak_src = bench.measured_peaks()
+    es = table.element_size()
+    isz = indices.element_size()
+    # per-rank algorithmic bytes of the local kernels (reference accounting)
+    fwd_bytes = es * w * local_nnz + 4 * w * batch      # rows gathered + fp32 partial written
+    bwd_bytes = es * w * (local_nnz + batch + num_unique) + 2 * isz * local_nnz
+    if rank == 0:
+        line = {
+            "metric": "lookups/s (fwd + transpose + bwd, compressed grad)",
+            "value": round(nnz / (ms_per_step * 1e-3), 1), "unit": "lookups/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "data": "synthetic",
+            "config": {"workload": f"row-sharded manual_benchmark shape: {world} shards of "
+                                   f"{shard_rows}x{w} {cfg['dtype']} (global {rows} rows), global batch "
+                                   f"{batch}, hotness {hot}, alpha {cfg['alpha']}, {cfg['index']} indices, "
+                                   f"sum, compressed grad",
+                       "parallelism": f"row-sharded x{world}: NCCL reduce-scatter of fp32 partial sums "
+                                      f"(forward), all-gather of grad_y (backward)",
+                       "l2": "flushed before every stage (512 MB write)",
+                       "nnz_global": nnz, "nnz_local_rank0": local_nnz, "num_unique_rank0": num_unique},
+            "stages": {"forward": {"ms": round(fwd_ms, 4)}, "transpose": {"ms": round(tr_ms, 4)},
+                       "backward": {"ms": round(bwd_ms, 4)},
+                       "collectives_alone_ms": {k: round(v, 4) for k, v in comm.items()}},
+            "roofline": {"bound": "hbm", "kernel": "BwdSegReduceKernel (local) + collectives",
+                         "achieved": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, 1),
+                         "peak": peak, "unit": "GB/s",
+                         "frac": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak, 4),
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "per-rank algorithmic bytes of forward+backward over their stage time "
+                                 "incl. the collectives"},
+            "cpu_baseline": None,
+            "e2e": {"value": (round(nnz / (e2e_ms * 1e-3), 1) if e2e_ms == e2e_ms else None),
+                    "unit": "lookups/s",
+                    "ms_per_step": (round(e2e_ms, 4) if e2e_ms == e2e_ms else None),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "wall_s_timed_region": round(wall, 3),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -153,6 +153,35 @@ int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
                         void* grad_embedding, void* inverse_mapping,
                         char* work, size_t* lwork, cuembed_stream_t stream);
 
+/*
+ * Row-sharded multi-GPU mode (new: the reference is single-GPU, README.md:110).
+ * A GPU that owns table rows [row_lo, row_hi) selects, from the replicated
+ * lookup indices of the global batch, the lookups that fall into its range:
+ * local_offsets [batch_size + 1] (int32 CSR offsets), local_indices (rebased
+ * to the shard: index - row_lo, same integer type as `indices`, capacity nnz)
+ * and local_weights keep bag order, so cuembed_forward / cuembed_transpose /
+ * cuembed_backward run unchanged on the shard.  Two-call workspace protocol.
+ */
+int cuembed_shard_select(const void* indices, int idx_type, const void* offsets,
+                         int off_type, const void* weights, int weight_dtype,
+                         int batch_size, int num_hots, long long row_lo,
+                         long long row_hi, int* local_offsets,
+                         void* local_indices, void* local_weights, char* work,
+                         size_t* lwork, cuembed_stream_t stream);
+
+/*
+ * Epilogue after the reduce-scatter of the fp32 partial sums: for the samples
+ * [sample0, sample0 + n_samples) of the global batch, out = partial (sum) or
+ * partial / global bag length (mean; / sum of weights if weights != NULL, zero
+ * vector if that sum is 0), cast to out_dtype.  offsets / num_hots / weights
+ * describe the GLOBAL batch.
+ */
+int cuembed_shard_finalize(const void* partial_f32, int n_samples,
+                           int embed_width, int mode, const void* offsets,
+                           int off_type, int num_hots, int sample0,
+                           const void* weights, int weight_dtype, void* out,
+                           int out_dtype, cuembed_stream_t stream);
+
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */
 unsigned long long cuembed_launch_count(void);
