@@ -519,6 +519,10 @@ def main():
     ap.add_argument("--cpu-sample-bags", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange fused over peer memory, or NCCL collectives")
+    ap.add_argument("--partial-dtype", default="f32", choices=["f32", "table"],
+                    help="N > 1, p2p: element type of the partial sums on the wire")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,6 +36,23 @@ SIGNATURES = {
                                    _vp, _vp, _szp, _vp]),
     "cuembed_shard_finalize": (_ci, [_vp, _ci, _ci, _ci, _vp, _ci, _ci, _ci, _vp,
                                      _ci, _vp, _ci, _vp]),
+    "cuembed_peer_alloc": (_ci, [_sz, ctypes.POINTER(_vp)]),
+    "cuembed_peer_free": (_ci, [_vp]),
+    "cuembed_peer_export": (_ci, [_vp, ctypes.c_char_p]),
+    "cuembed_peer_open": (_ci, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "cuembed_peer_close": (_ci, [_vp]),
+    "cuembed_shard_pool_push": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci,
+                                      ctypes.c_longlong, ctypes.c_longlong,
+                                      ctypes.POINTER(_vp), _ci, _ci, _ci, _vp, _vp]),
+    "cuembed_shard_concat_push": (_ci, [_vp, _ci, _ci, _vp, _ci, _ci, _ci,
+                                        ctypes.c_longlong, ctypes.c_longlong,
+                                        ctypes.POINTER(_vp), _ci, _ci, _vp]),
+    "cuembed_shard_signal": (_ci, [ctypes.POINTER(_vp), _ci, _ci, _ci, ctypes.c_uint, _vp]),
+    "cuembed_shard_wait": (_ci, [_vp, _ci, _ci, ctypes.c_uint, _vp]),
+    "cuembed_shard_reduce_finalize": (_ci, [_vp, _ci, _ci, _vp, _ci, ctypes.c_uint, _ci,
+                                            _ci, _ci, _vp, _ci, _ci, _ci, _vp, _ci, _vp,
+                                            _ci, _vp]),
+    "cuembed_shard_allgather_push": (_ci, [_vp, _sz, ctypes.POINTER(_vp), _ci, _ci, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }
 

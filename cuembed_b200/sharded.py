@@ -12,6 +12,17 @@ New functionality relative to the reference, which is single-table single-GPU
     the ordinary transpose + backward on the rank's own lookups -- gradients
     never leave the owning shard.
 
+Two transports for the exchange step:
+
+  * "p2p" (default on CUDA when the ranks can map each other's memory): the
+    exchange is fused into the kernels over NVLink / NVSwitch peer memory
+    (csrc/sharded_p2p.cu) -- the pooling kernel stores every partial row
+    straight into the bag owner's slot while it gathers, the owner sums the
+    slots in rank order (deterministic), grad_y slices are pushed by the copy
+    engines while the local transpose runs; no collective call on the data path;
+  * "nccl": reduce-scatter / all-gather through torch.distributed (the
+    baseline, and what the gloo host-logic tests exercise on CPU).
+
 The local compute is the single-GPU library (C ABI) on the rank's compact local
 CSR produced by cuembed_shard_select.  `ops` is injectable so that the host
 logic (partitioning, collectives, epilogue rules) can be exercised with gloo on
@@ -82,18 +93,18 @@ class CudaLocalOps:
                                weights, out)
         return out
 
-    def local_backward(self, grad_y, local_offsets, local_indices, local_weights,
-                       batch, local_nnz, num_local_rows, compressed):
+    def local_transpose(self, local_offsets, local_indices, local_weights, batch,
+                        local_nnz, compressed, sample_ids=None):
+        """Row ids + stable sort (+ compressed remap) of the rank's own lookups;
+        independent of grad_y.  Returns (t_idx, t_sid, t_w, remapped)."""
         api = self.api
-        dev = grad_y.device
-        width = grad_y.shape[1]
+        dev = local_indices.device
         idt = local_indices.dtype
-        if local_nnz == 0:
-            rows = 0 if compressed else num_local_rows
-            return (torch.zeros(rows, width, dtype=grad_y.dtype, device=dev),
-                    torch.empty(0, dtype=idt, device=dev) if compressed else None)
-        row_ids = torch.empty(local_nnz, dtype=idt, device=dev)
-        api.ExtractRowIdsFromCSR(local_offsets, batch, row_ids)
+        if sample_ids is None:
+            row_ids = torch.empty(local_nnz, dtype=idt, device=dev)
+            api.ExtractRowIdsFromCSR(local_offsets, batch, row_ids)
+        else:
+            row_ids = sample_ids
         t_idx = torch.empty(local_nnz, dtype=idt, device=dev)
         t_sid = torch.empty(local_nnz, dtype=idt, device=dev)
         t_w = torch.empty(local_nnz, dtype=local_weights.dtype, device=dev) \
@@ -104,17 +115,43 @@ class CudaLocalOps:
                      api.ComputeCompressedGradIndices(idx, local_nnz, None, None))
         work = self._scratch("transpose", nbytes, dev)
         api.Transpose(row_ids, idx, w, local_nnz, t_idx, t_sid, t_w, work)
-        remapped, inv = None, None
-        rows = num_local_rows
+        remapped = None
         if compressed:
             remapped = torch.empty(local_nnz, dtype=idt, device=dev)
             api.ComputeCompressedGradIndices(t_idx, local_nnz, remapped, work)
-            rows = int(remapped[-1].item()) + 1  # the caller sizes the gradient
-            inv = torch.empty(rows, dtype=idt, device=dev)
-        grad = torch.empty(rows, width, dtype=grad_y.dtype, device=dev)
+        return t_idx, t_sid, t_w, remapped
+
+    def local_backward_coo(self, grad_y, coo, local_nnz, num_local_rows,
+                           grad=None, inv=None):
+        """`grad` / `inv` may be preallocated by a caller that already knows the
+        number of unique rows (saves the host read of remapped[-1])."""
+        api = self.api
+        t_idx, t_sid, t_w, remapped = coo
+        dev = grad_y.device
+        width = grad_y.shape[1]
+        if grad is None:
+            rows = num_local_rows
+            if remapped is not None:
+                rows = int(remapped[-1].item()) + 1  # the caller sizes the gradient
+                inv = torch.empty(rows, dtype=t_idx.dtype, device=dev)
+            grad = torch.empty(rows, width, dtype=grad_y.dtype, device=dev)
+        rows = grad.shape[0]
         api.EmbeddingBackward(grad_y, width, rows, local_nnz, t_idx, t_sid, remapped,
                               t_w, False, grad, inv)
         return grad, inv
+
+    def local_backward(self, grad_y, local_offsets, local_indices, local_weights,
+                       batch, local_nnz, num_local_rows, compressed):
+        dev = grad_y.device
+        width = grad_y.shape[1]
+        idt = local_indices.dtype
+        if local_nnz == 0:
+            rows = 0 if compressed else num_local_rows
+            return (torch.zeros(rows, width, dtype=grad_y.dtype, device=dev),
+                    torch.empty(0, dtype=idt, device=dev) if compressed else None)
+        coo = self.local_transpose(local_offsets, local_indices, local_weights, batch,
+                                   local_nnz, compressed)
+        return self.local_backward_coo(grad_y, coo, local_nnz, num_local_rows)
 
 
 @dataclass

@@ -53,6 +53,228 @@ def unique_bags_torch(gen, batch, hot, num_categories, alpha, device):
 
 
 def run(args, rank, local_rank, world):
+    """Dispatch on --transport: "p2p" (default: exchange fused into the kernels
+    over peer memory) or "nccl" (reduce-scatter / all-gather baseline).  If the
+    ranks cannot map each other's memory the p2p request falls back to nccl and
+    says so in the JSON line."""
+    transport = getattr(args, "transport", "p2p")
+    note = None
+    if transport == "p2p":
+        ok = torch.tensor([1], device=torch.device("cuda", local_rank))
+        try:
+            from . import peer
+            probe = peer.PeerBuffer(4096)
+            probe.close()
+        except Exception as e:  # noqa: BLE001 -- any failure means "cannot map"
+            ok.zero_()
+            note = f"{type(e).__name__}: {e}"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            return run_p2p(args, rank, local_rank, world)
+        note = f"nccl (peer mapping unavailable: {note})"
+    return run_nccl(args, rank, local_rank, world, note)
+
+
+def make_inputs(args, rank, world, dev):
+    import bench
+    from cuembed_b200.sharded import row_range
+    cfg = dict(bench.WORKLOADS[args.workload])
+    tdt = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[cfg["dtype"]]
+    idt = torch.int32 if cfg["index"] == "int32" else torch.int64
+    shard_rows, w, hot = cfg["num_categories"], cfg["embed_width"], cfg["hotness"]
+    rows = shard_rows * world
+    batch = cfg["batch_size"] * world
+    nnz = batch * hot
+    lo, hi = row_range(rows, world, rank)
+    indices = torch.empty(nnz, dtype=idt, device=dev)
+    if rank == 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234)
+        indices.copy_(unique_bags_torch(g, batch, hot, rows, cfg["alpha"], dev).view(-1).to(idt))
+    dist.broadcast(indices, src=0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(123456 + rank)
+    table = torch.empty(hi - lo, w, dtype=tdt, device=dev)
+    for r0 in range(0, hi - lo, 1 << 20):
+        r1 = min(hi - lo, r0 + (1 << 20))
+        table[r0:r1] = (torch.rand(r1 - r0, w, generator=g, device=dev) * 2 - 1).to(tdt)
+    per = batch // world
+    g.manual_seed(654321 + rank)
+    grad_slice = torch.randint(-10, 11, (per, w), generator=g, device=dev).to(tdt)
+    return cfg, tdt, idt, rows, batch, nnz, per, indices, table, grad_slice
+
+
+def run_p2p(args, rank, local_rank, world):
+    """One step = forward (pool + push over NVLink, signal, rank-ordered reduce)
+    -> [copy engines push grad_y slices || select + sort of the own lookups]
+    -> wait -> backward.  The WHOLE step is timed with one CUDA-event pair (L2
+    flushed and ranks aligned before it), max over ranks; the split into stages
+    comes from events recorded inside the step."""
+    import bench
+    import cuembed_b200 as ce
+    from cuembed_b200.sharded_p2p import PeerShardedEmbedding
+
+    dev = torch.device("cuda", local_rank)
+    cfg, tdt, idt, rows, batch, nnz, per, indices, table, grad_slice = \
+        make_inputs(args, rank, world, dev)
+    w, hot = cfg["embed_width"], cfg["hotness"]
+    shard_rows = cfg["num_categories"]
+    pdt = {"f32": torch.float32, "table": tdt}[getattr(args, "partial_dtype", "f32")]
+    emb = PeerShardedEmbedding(table, rows, partial_dtype=pdt)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    # sizes that a training loop knows from the previous identical step
+    out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+    emb.prepare_backward(ctx, True)
+    local_nnz = ctx.local_nnz
+    num_unique = int(ctx.coo[3][-1].item()) + 1
+    grad = torch.zeros(num_unique, w, dtype=tdt, device=dev)
+    inv = torch.empty(num_unique, dtype=idt, device=dev)
+    g2, _ = emb.backward(grad_slice, ctx)
+    torch.cuda.synchronize()
+    state = {}
+
+    def one_step(rec=None):
+        flush.fill_(1)
+        dist.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+        ev[1].record(stream)
+        pend = emb.backward_begin(grad_slice, ctx, True, local_nnz=local_nnz)
+        ev[2].record(stream)
+        emb.backward_finish(pend, grad=grad, inverse=inv)
+        ev[3].record(stream)
+        state["out"] = out
+        if rec is not None:
+            rec.append(ev)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ce.launch_count()
+    events = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(events)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    launches = ce.launch_count() - launches0
+    acc = [0.0, 0.0, 0.0, 0.0]
+    for ev in events:
+        acc[0] += ev[0].elapsed_time(ev[3])
+        acc[1] += ev[0].elapsed_time(ev[1])
+        acc[2] += ev[1].elapsed_time(ev[2])
+        acc[3] += ev[2].elapsed_time(ev[3])
+    t = torch.tensor([a / args.steps for a in acc], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, fwd_ms, tr_ms, bwd_ms = (float(x) for x in t.tolist())
+    status = emb.status()
+
+    # end to end with host buffers: indices + grad slice in, output slice +
+    # compressed gradient + row list out
+    e2e_ms = float("nan")
+    h2d = d2h = 0
+    if not args.no_e2e:
+        idx_host = indices.cpu().pin_memory()
+        gy_host = grad_slice.cpu().pin_memory()
+        out_host = torch.empty(per, w, dtype=tdt).pin_memory()
+        grad_host = torch.empty(num_unique, w, dtype=tdt).pin_memory()
+        inv_host = torch.empty(num_unique, dtype=idt).pin_memory()
+
+        def e2e_step():
+            indices.copy_(idx_host, non_blocking=True)
+            out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+            out_host.copy_(out, non_blocking=True)
+            grad_slice.copy_(gy_host, non_blocking=True)
+            pend = emb.backward_begin(grad_slice, ctx, True, local_nnz=local_nnz)
+            emb.backward_finish(pend, grad=grad, inverse=inv)
+            grad_host.copy_(grad, non_blocking=True)
+            inv_host.copy_(inv, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        c = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        e2e_ms = float(c.item())
+        es = table.element_size()
+        h2d = world * (nnz * indices.element_size() + per * w * es)
+        d2h = world * (per * w * es + num_unique * (w * es + indices.element_size()))
+
+    clocks = sampler.stop() if rank == 0 else None
+    peak, peak_src = bench.measured_peaks()
+    es = table.element_size()
+    isz = indices.element_size()
+    psz = torch.empty(0, dtype=pdt).element_size()
+    # per-rank algorithmic bytes of the local kernels (reference accounting):
+    # rows gathered + partial rows written / received + gradient traffic
+    fwd_bytes = es * w * local_nnz + psz * w * batch + psz * w * per * world + es * w * per
+    bwd_bytes = es * w * (local_nnz + batch + num_unique) + 2 * isz * local_nnz
+    nvlink_fwd = psz * w * per * (world - 1)
+    nvlink_bwd = es * w * per * (world - 1)
+    if rank == 0:
+        achieved = (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
+        line = {
+            "metric": "lookups/s (fwd + transpose + bwd, compressed grad)",
+            "value": round(nnz / (ms_per_step * 1e-3), 1), "unit": "lookups/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "data": "synthetic",
+            "config": {"workload": f"row-sharded manual_benchmark shape: {world} shards of "
+                                   f"{shard_rows}x{w} {cfg['dtype']} (global {rows} rows), global batch "
+                                   f"{batch}, hotness {hot}, alpha {cfg['alpha']}, {cfg['index']} indices, "
+                                   f"sum, compressed grad",
+                       "parallelism": f"row-sharded x{world}, exchange fused over NVLink peer memory: "
+                                      f"pool kernel stores {('fp32' if psz == 4 else cfg['dtype'])} partial "
+                                      f"rows into the bag owner's slots, rank-ordered reduce; grad_y "
+                                      f"slices pushed by copy engines during the local sort",
+                       "transport": "p2p",
+                       "l2": "flushed before every step (512 MB write)",
+                       "nnz_global": nnz, "nnz_local_rank0": local_nnz,
+                       "num_unique_rank0": num_unique,
+                       "nvlink_bytes_out_per_rank": {"forward": nvlink_fwd, "backward": nvlink_bwd},
+                       "peer_wait_status": status},
+            "stages": {"forward": {"ms": round(fwd_ms, 4)},
+                       "select_sort_with_grad_push": {"ms": round(tr_ms, 4)},
+                       "backward": {"ms": round(bwd_ms, 4)}},
+            "roofline": {"bound": "hbm", "kernel": "ShardPoolPushKernel + BwdSegReduceKernel (local)",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "per-rank algorithmic bytes of forward+backward over their in-step "
+                                 "time incl. the NVLink exchange"},
+            "cpu_baseline": None,
+            "e2e": {"value": (round(nnz / (e2e_ms * 1e-3), 1) if e2e_ms == e2e_ms else None),
+                    "unit": "lookups/s",
+                    "ms_per_step": (round(e2e_ms, 4) if e2e_ms == e2e_ms else None),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "wall_s_timed_region": round(wall, 3),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    emb.close()
+    dist.destroy_process_group()
+
+
+def run_nccl(args, rank, local_rank, world, transport_note=None):
     import bench
     import cuembed_b200 as ce
     from cuembed_b200.sharded import RowShardedEmbedding, row_range
@@ -243,6 +465,7 @@ def run(args, rank, local_rank, world):
                                    f"sum, compressed grad",
                        "parallelism": f"row-sharded x{world}: NCCL reduce-scatter of fp32 partial sums "
                                       f"(forward), all-gather of grad_y (backward)",
+                       "transport": transport_note or "nccl",
                        "l2": "flushed before every stage (512 MB write)",
                        "nnz_global": nnz, "nnz_local_rank0": local_nnz, "num_unique_rank0": num_unique},
             "stages": {"forward": {"ms": round(fwd_ms, 4)}, "transpose": {"ms": round(tr_ms, 4)},

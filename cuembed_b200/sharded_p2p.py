@@ -1,0 +1,298 @@
+"""Row-sharded embedding with the exchange fused into the kernels over NVLink /
+NVSwitch peer memory (csrc/sharded_p2p.cu); same interface as
+cuembed_b200.sharded.RowShardedEmbedding, no collective call on the data path.
+
+forward   cuembed_shard_pool_push  (gather + pool + store into the bag owner's
+          slot over NVLink) -> cuembed_shard_signal -> cuembed_shard_reduce_finalize
+          (wait for all ranks, sum the slots in rank order, mean by the global
+          bag length, cast).
+          concat: cuembed_shard_concat_push writes every looked-up row to its
+          final place in the bag owner's output (all-to-all made of stores).
+backward  the grad_y slice is pushed to every rank by the copy engines on a
+          side stream (cuembed_shard_allgather_push + signal) WHILE the main
+          stream selects and sorts the rank's own lookups; cuembed_shard_wait;
+          ordinary deterministic backward on the owner.  Gradients never leave
+          the owning shard.
+
+Exchange buffers are double-buffered by epoch parity (see the protocol note in
+csrc/sharded_p2p.cu); every rank must call forward / backward the same number
+of times, as with any collective.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, peer
+from .api import CombineMode, CuEmbedError, _check, _dev, _dt, _it, _stream
+from .sharded import CudaLocalOps, row_range
+
+CH_FORWARD, CH_GRAD, CH_CONCAT = 0, 1, 2
+
+
+@dataclass
+class PeerForwardContext:
+    indices: torch.Tensor
+    offsets: Optional[torch.Tensor]
+    weights: Optional[torch.Tensor]
+    counts: Optional[torch.Tensor]
+    batch: int
+    num_hots: int
+    mode: CombineMode
+    coo: Optional[tuple] = None
+    local_nnz: int = -1
+
+
+class PeerShardedEmbedding:
+    """One rank's shard; exchange through peer memory.
+
+    `buffers(kind, nbytes)` returns this rank's view of a symmetric allocation
+    (peer.PeerBuffer by default; tests pass peer.LocalPeerGroup views together
+    with explicit `rank` / `world` to run several virtual ranks in one process).
+    partial_dtype: torch.float32 (default: exact fp32 partial sums on the wire)
+    or the table's 16-bit dtype (half the NVLink bytes, one extra rounding per
+    partial sum).
+    """
+
+    def __init__(self, local_table: torch.Tensor, num_rows: int,
+                 group: Optional[dist.ProcessGroup] = None,
+                 partial_dtype: torch.dtype = torch.float32,
+                 rank: Optional[int] = None, world: Optional[int] = None,
+                 buffers: Optional[Callable] = None):
+        if not local_table.is_cuda:
+            raise CuEmbedError("PeerShardedEmbedding needs CUDA tensors: there is no CPU path")
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.num_rows = num_rows
+        self.lo, self.hi = row_range(num_rows, self.world, self.rank)
+        if local_table.shape[0] != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} owns rows [{self.lo}, {self.hi}) but the "
+                             f"local table has {local_table.shape[0]} rows")
+        self.table = local_table
+        self.device = local_table.device
+        self.partial_dtype = partial_dtype
+        self.ops = CudaLocalOps()
+        self._lib = _lib.load()
+        self._buffers = buffers if buffers is not None else \
+            (lambda kind, nbytes: peer.PeerBuffer(nbytes, group, self.device))
+        self._bufs = {}
+        self._epoch = {CH_FORWARD: 0, CH_GRAD: 0, CH_CONCAT: 0}
+        self._side = torch.cuda.Stream(device=self.device)
+        self._flags = self._buffers("flags", peer.FLAG_BYTES)
+        self._flag_ptrs = peer.ptr_array(self._flags.ptrs)
+
+    # ------------------------------------------------------------ plumbing
+    def _buffer(self, kind: str, nbytes: int):
+        buf = self._bufs.get(kind)
+        if buf is None or buf.nbytes < nbytes:
+            if buf is not None:
+                buf.close()
+            buf = self._buffers(kind, nbytes)
+            self._bufs[kind] = buf
+        return buf
+
+    def _signal(self, channel: int, epoch: int, stream) -> None:
+        _check(self._lib.cuembed_shard_signal(self._flag_ptrs, self.world, self.rank,
+                                              channel, epoch, _stream(stream)))
+
+    def status(self) -> int:
+        """0, or 1 + the rank a wait gave up on (needs a prior synchronize)."""
+        word = peer.CHANNELS * peer.MAX_WORLD
+        return int(self._flags.tensor(4 * word, (1,), torch.int32).item())
+
+    def close(self) -> None:
+        for buf in self._bufs.values():
+            buf.close()
+        self._bufs = {}
+        self._flags.close()
+
+    # ------------------------------------------------------------- forward
+    def forward(self, indices, offsets, weights, batch_size: int, num_hots: int,
+                mode: CombineMode = CombineMode.kSum,
+                out_dtype: Optional[torch.dtype] = None, stream=None):
+        """Pooled lookup of the GLOBAL batch (replicated indices); returns this
+        rank's slice [batch/world, width] (concat: [batch/world * hots, width])
+        and the context for backward."""
+        return self.forward_finish(self.forward_begin(
+            indices, offsets, weights, batch_size, num_hots, mode, out_dtype, stream))
+
+    def forward_begin(self, indices, offsets, weights, batch_size: int, num_hots: int,
+                      mode: CombineMode = CombineMode.kSum,
+                      out_dtype: Optional[torch.dtype] = None, stream=None):
+        """Push phase (never waits for another rank).  Returns a pending handle
+        for forward_finish."""
+        if batch_size % self.world != 0:
+            raise ValueError("batch_size must be divisible by the number of ranks")
+        if weights is not None and weights.dtype != self.table.dtype:
+            raise CuEmbedError("weights must have the element type of the table")
+        if mode == CombineMode.kConcat:
+            return self._concat_begin(indices, offsets, weights, batch_size, num_hots,
+                                      stream)
+        lib = self._lib
+        width = self.table.shape[1]
+        per = batch_size // self.world
+        out_dtype = self.table.dtype if out_dtype is None else out_dtype
+        psize = torch.empty(0, dtype=self.partial_dtype).element_size()
+        one = self.world * per * width * psize
+        buf = self._buffer("slots", 2 * one)
+        self._epoch[CH_FORWARD] += 1
+        epoch = self._epoch[CH_FORWARD]
+        base = (epoch & 1) * one
+        slot_ptrs = peer.ptr_array(buf.ptrs, base + self.rank * per * width * psize)
+        counts = torch.empty(batch_size, dtype=torch.int32, device=self.device)
+        _check(lib.cuembed_shard_pool_push(
+            _dev(self.table, "table"), _dt(self.table), width,
+            _dev(indices, "indices"), _it(indices), _dev(offsets, "offsets"),
+            _it(offsets) if offsets is not None else 0, _dev(weights, "weights"),
+            batch_size, num_hots, self.lo, self.hi, slot_ptrs, self.world, self.rank,
+            _dt(torch.empty(0, dtype=self.partial_dtype)), _dev(counts, "counts"),
+            _stream(stream)))
+        self._signal(CH_FORWARD, epoch, stream)
+        ctx = PeerForwardContext(indices, offsets, weights, counts, batch_size,
+                                 num_hots, mode)
+        return ("pool", ctx, buf, base, epoch, out_dtype, stream)
+
+    def forward_finish(self, pending):
+        """Wait for every rank's pushes, reduce in rank order, epilogue."""
+        if pending[0] == "concat":
+            return self._concat_finish(pending)
+        _, ctx, buf, base, epoch, out_dtype, stream = pending
+        lib = self._lib
+        width = self.table.shape[1]
+        per = ctx.batch // self.world
+        offsets, weights, num_hots, mode = ctx.offsets, ctx.weights, ctx.num_hots, ctx.mode
+        out = torch.empty(per, width, dtype=out_dtype, device=self.device)
+        _check(lib.cuembed_shard_reduce_finalize(
+            buf.local + base, _dt(torch.empty(0, dtype=self.partial_dtype)), self.world,
+            self._flags.local, CH_FORWARD, epoch, per, width, int(mode),
+            _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+            num_hots, self.rank * per, _dev(weights, "weights"),
+            _dt(weights) if weights is not None else 0, _dev(out, "out"), _dt(out),
+            _stream(stream)))
+        return out, ctx
+
+    def _concat_begin(self, indices, offsets, weights, batch_size, num_hots, stream):
+        if weights is not None:
+            raise CuEmbedError("Check failed: weights == nullptr || mode != CombineMode::kConcat")
+        if offsets is not None or num_hots <= 0:
+            raise CuEmbedError("Check failed: offsets == nullptr || mode != CombineMode::kConcat")
+        lib = self._lib
+        width = self.table.shape[1]
+        per = batch_size // self.world
+        one = per * num_hots * width * self.table.element_size()
+        buf = self._buffer("concat", 2 * one)
+        self._epoch[CH_CONCAT] += 1
+        epoch = self._epoch[CH_CONCAT]
+        base = (epoch & 1) * one
+        _check(lib.cuembed_shard_concat_push(
+            _dev(self.table, "table"), _dt(self.table), width, _dev(indices, "indices"),
+            _it(indices), batch_size, num_hots, self.lo, self.hi,
+            peer.ptr_array(buf.ptrs, base), self.world, self.rank, _stream(stream)))
+        self._signal(CH_CONCAT, epoch, stream)
+        ctx = PeerForwardContext(indices, None, None, None, batch_size, num_hots,
+                                 CombineMode.kConcat)
+        return ("concat", ctx, buf, base, epoch, None, stream)
+
+    def _concat_finish(self, pending):
+        _, ctx, buf, base, epoch, _, stream = pending
+        lib = self._lib
+        width = self.table.shape[1]
+        per = ctx.batch // self.world
+        num_hots = ctx.num_hots
+        _check(lib.cuembed_shard_wait(self._flags.local, self.world, CH_CONCAT, epoch,
+                                      _stream(stream)))
+        # valid until the next-but-one concat forward (double buffer)
+        out = buf.tensor(base, (per * num_hots, width), self.table.dtype)
+        return out, ctx
+
+    # ------------------------------------------------------------ backward
+    def prepare_backward(self, ctx: PeerForwardContext, compressed: bool = True,
+                         local_nnz: Optional[int] = None) -> None:
+        """Select + sort the rank's own lookups (independent of grad_y; called by
+        backward if the caller has not done it earlier).  `local_nnz`: the
+        number of lookups this rank owns if the caller already knows it (saves
+        one host read)."""
+        if ctx.coo is not None:
+            return
+        concat = ctx.mode == CombineMode.kConcat
+        weights = ctx.weights
+        if concat:
+            # the sample id of a concat lookup is its position in the global
+            # index list: carry it through the select as a 4-byte payload
+            if ctx.indices.numel() >= 2 ** 31:
+                raise CuEmbedError("sharded concat backward needs nnz < 2^31")
+            weights = torch.arange(ctx.indices.numel(), dtype=torch.int32,
+                                   device=self.device).view(torch.float32)
+        l_off, l_idx, l_w = self.ops.shard_select(ctx.indices, ctx.offsets, weights,
+                                                  ctx.batch, ctx.num_hots, self.lo, self.hi)
+        ctx.local_nnz = int(l_off[-1].item()) if local_nnz is None else int(local_nnz)
+        if ctx.local_nnz == 0:
+            ctx.coo = ()
+            return
+        sample_ids = None
+        if concat:
+            sample_ids = l_w[:ctx.local_nnz].view(torch.int32).to(l_idx.dtype)
+            l_w = None
+        ctx.coo = self.ops.local_transpose(l_off, l_idx, l_w, ctx.batch, ctx.local_nnz,
+                                           compressed, sample_ids=sample_ids)
+
+    def backward(self, grad_out_slice: torch.Tensor, ctx: PeerForwardContext,
+                 compressed: bool = True):
+        """grad_out_slice: this rank's slice of dL/dout.  Returns (grad, rows):
+        gradient rows for this shard and, if compressed, the GLOBAL table row of
+        each gradient row."""
+        return self.backward_finish(self.backward_begin(grad_out_slice, ctx, compressed))
+
+    def backward_begin(self, grad_out_slice: torch.Tensor, ctx: PeerForwardContext,
+                       compressed: bool = True, local_nnz: Optional[int] = None):
+        """Push phase: copy engines send the slice to every rank (side stream)
+        while the main stream selects and sorts; never waits for another rank."""
+        lib = self._lib
+        grad_out_slice = grad_out_slice.contiguous()
+        width = grad_out_slice.shape[1]
+        n_slice = grad_out_slice.shape[0]
+        es = grad_out_slice.element_size()
+        one = self.world * n_slice * width * es
+        buf = self._buffer("gather", 2 * one)
+        self._epoch[CH_GRAD] += 1
+        epoch = self._epoch[CH_GRAD]
+        base = (epoch & 1) * one
+        main = torch.cuda.current_stream(self.device)
+        # copy engines push the slice to every rank while the SMs sort
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            _check(lib.cuembed_shard_allgather_push(
+                _dev(grad_out_slice, "grad_out_slice"), n_slice * width * es,
+                peer.ptr_array(buf.ptrs, base), self.world, self.rank,
+                self._side.cuda_stream))
+            self._signal(CH_GRAD, epoch, self._side)
+        grad_out_slice.record_stream(self._side)
+        self.prepare_backward(ctx, compressed, local_nnz)
+        return (grad_out_slice, ctx, compressed, buf, base, epoch)
+
+    def backward_finish(self, pending, grad=None, inverse=None):
+        """`grad` [num_unique or shard rows, width] / `inverse` [num_unique]:
+        optional preallocated outputs (then nothing is read back to size them)."""
+        grad_out_slice, ctx, compressed, buf, base, epoch = pending
+        lib = self._lib
+        width = grad_out_slice.shape[1]
+        n_slice = grad_out_slice.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        _check(lib.cuembed_shard_wait(self._flags.local, self.world, CH_GRAD, epoch,
+                                      main.cuda_stream))
+        main.wait_stream(self._side)  # the local slice was copied on the side stream
+        if ctx.local_nnz == 0:
+            rows = 0 if compressed else self.hi - self.lo
+            idt = ctx.indices.dtype
+            return (torch.zeros(rows, width, dtype=grad_out_slice.dtype, device=self.device),
+                    torch.empty(0, dtype=idt, device=self.device) if compressed else None)
+        full = buf.tensor(base, (self.world * n_slice, width), grad_out_slice.dtype)
+        grad, inv = self.ops.local_backward_coo(full, ctx.coo, ctx.local_nnz,
+                                                self.hi - self.lo, grad, inverse)
+        rows = inv + self.lo if inv is not None else None
+        return grad, rows

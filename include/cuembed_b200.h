@@ -182,6 +182,94 @@ int cuembed_shard_finalize(const void* partial_f32, int n_samples,
                            const void* weights, int weight_dtype, void* out,
                            int out_dtype, cuembed_stream_t stream);
 
+/*
+ * Row-sharded mode, exchange fused with the kernels over NVLink / NVSwitch peer
+ * memory (one process per GPU; no collective library call on the data path).
+ *
+ * Peer memory: cuembed_peer_alloc returns zero-filled device memory that can
+ * be exported (cuembed_peer_export -> an opaque CUEMBED_PEER_HANDLE_BYTES
+ * handle to ship to the other processes by any means) and mapped by them
+ * (cuembed_peer_open; cuembed_peer_close unmaps).  The functions below take
+ * HOST arrays of `world` device pointers, entry o being rank o's buffer as
+ * mapped in the calling process (the caller's own buffer at entry `rank`).
+ *
+ * Flag buffer: every rank owns CUEMBED_PEER_FLAG_BYTES of peer memory:
+ * uint32 flags[CUEMBED_PEER_CHANNELS][CUEMBED_MAX_WORLD] followed by one
+ * uint32 status word (non-zero after a wait timed out).  cuembed_shard_signal
+ * release-stores `epoch` into flags[channel][rank] of every rank;
+ * waits succeed once all `world` flags of the channel reached `epoch`.
+ */
+#define CUEMBED_MAX_WORLD 16
+#define CUEMBED_PEER_HANDLE_BYTES 64
+#define CUEMBED_PEER_CHANNELS 4
+#define CUEMBED_PEER_FLAG_BYTES 512
+
+int cuembed_peer_alloc(size_t bytes, void** ptr);
+int cuembed_peer_free(void* ptr);
+int cuembed_peer_export(void* ptr, unsigned char* handle);
+int cuembed_peer_open(const unsigned char* handle, void** ptr);
+int cuembed_peer_close(void* ptr);
+
+/*
+ * Forward, step 1: pool the lookups of the GLOBAL batch (replicated indices /
+ * offsets / weights, batch_size % world == 0) that fall into this rank's rows
+ * [row_lo, row_hi) -- local_params holds exactly those rows -- in bag order
+ * with fp32 accumulation, and store each partial row directly into the
+ * exchange buffer of the rank that owns the bag:
+ *   slot_ptrs[o] + (rank * per + bag - o * per) * embed_width   (partial_dtype
+ * elements, per = batch_size / world, o = bag / per).
+ * counts (optional, [batch_size] int32) receives the number of lookups of each
+ * bag that this rank owns.
+ */
+int cuembed_shard_pool_push(const void* local_params, int in_dtype,
+                            int embed_width, const void* indices, int idx_type,
+                            const void* offsets, int off_type,
+                            const void* weights, int batch_size, int num_hots,
+                            long long row_lo, long long row_hi,
+                            void* const* slot_ptrs, int world, int rank,
+                            int partial_dtype, int* counts,
+                            cuembed_stream_t stream);
+
+/* Sharded concat (fixed hotness): the owner of each looked-up row copies it to
+ * out_ptrs[o] + ((b - o * per) * num_hots + j) * embed_width, o = b / per. */
+int cuembed_shard_concat_push(const void* local_params, int dtype,
+                              int embed_width, const void* indices,
+                              int idx_type, int batch_size, int num_hots,
+                              long long row_lo, long long row_hi,
+                              void* const* out_ptrs, int world, int rank,
+                              cuembed_stream_t stream);
+
+/* Tell every rank that this rank's pushes of `epoch` are complete (enqueue
+ * after the pushing kernel / copies on the same stream). */
+int cuembed_shard_signal(void* const* flag_ptrs, int world, int rank,
+                         int channel, unsigned epoch, cuembed_stream_t stream);
+/* Hold the stream until all ranks signalled `epoch` on `channel`. */
+int cuembed_shard_wait(const void* flags, int world, int channel,
+                       unsigned epoch, cuembed_stream_t stream);
+
+/*
+ * Forward, step 2 (on the bag owner): wait for all ranks, then
+ * out[s, :] = cast(scale * (slot 0 + slot 1 + ... in rank order)) for the
+ * samples [sample0, sample0 + n_samples) of the global batch; slots is this
+ * rank's exchange buffer [world][n_samples][embed_width] of partial_dtype;
+ * scale as in cuembed_shard_finalize.
+ */
+int cuembed_shard_reduce_finalize(const void* slots, int partial_dtype,
+                                  int world, const void* flags, int channel,
+                                  unsigned epoch, int n_samples,
+                                  int embed_width, int mode,
+                                  const void* offsets, int off_type,
+                                  int num_hots, int sample0,
+                                  const void* weights, int weight_dtype,
+                                  void* out, int out_dtype,
+                                  cuembed_stream_t stream);
+
+/* Backward: copy this rank's `bytes` of grad_y into every rank's gather buffer
+ * at offset rank * bytes (copy engines; follow with cuembed_shard_signal). */
+int cuembed_shard_allgather_push(const void* src, size_t bytes,
+                                 void* const* gather_ptrs, int world, int rank,
+                                 cuembed_stream_t stream);
+
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */
 unsigned long long cuembed_launch_count(void);
