@@ -519,6 +519,8 @@ def main():
     ap.add_argument("--cpu-sample-bags", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", default=None,
+                    help="N > 1: write a CUPTI per-kernel time table of 5 extra steps here")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange fused over peer memory, or NCCL collectives")
     ap.add_argument("--partial-dtype", default="f32", choices=["f32", "table"],

@@ -34,6 +34,9 @@ SIGNATURES = {
     "cuembed_shard_select": (_ci, [_vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
                                    ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                    _vp, _vp, _szp, _vp]),
+    "cuembed_shard_select_coo": (_ci, [_vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
+                                       ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
+                                       _vp, _vp, _vp, _vp, _szp, _vp]),
     "cuembed_shard_finalize": (_ci, [_vp, _ci, _ci, _ci, _vp, _ci, _ci, _ci, _vp,
                                      _ci, _vp, _ci, _vp]),
     "cuembed_peer_alloc": (_ci, [_sz, ctypes.POINTER(_vp)]),

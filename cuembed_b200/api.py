@@ -246,6 +246,33 @@ def ShardSelect(indices: torch.Tensor, offsets: Optional[torch.Tensor],
     return int(lwork.value)
 
 
+def ShardSelectCoo(indices: torch.Tensor, offsets: Optional[torch.Tensor],
+                   weights: Optional[torch.Tensor], batch_size: int, num_hots: int,
+                   row_lo: int, row_hi: int, counts: Optional[torch.Tensor],
+                   local_offsets: torch.Tensor, local_indices: torch.Tensor,
+                   local_sample_ids: Optional[torch.Tensor],
+                   local_weights: Optional[torch.Tensor], work: torch.Tensor,
+                   stream=None) -> None:
+    """cuembed_shard_select_coo: like ShardSelect, optionally reusing per-bag
+    counts and writing the sample id of every selected lookup."""
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(work.numel())
+    if local_offsets.dtype != torch.int32:
+        raise CuEmbedError("local_offsets must be int32")
+    if counts is not None and counts.dtype != torch.int32:
+        raise CuEmbedError("counts must be int32")
+    if local_sample_ids is not None and local_sample_ids.dtype != indices.dtype:
+        raise CuEmbedError("local_sample_ids must have the dtype of indices")
+    _check(lib.cuembed_shard_select_coo(
+        _dev(indices, "indices"), _it(indices), _dev(offsets, "offsets"),
+        _it(offsets) if offsets is not None else 0, _dev(weights, "weights"),
+        _dt(weights) if weights is not None else 0, int(batch_size), int(num_hots),
+        int(row_lo), int(row_hi), _dev(counts, "counts"),
+        _dev(local_offsets, "local_offsets"), _dev(local_indices, "local_indices"),
+        _dev(local_sample_ids, "local_sample_ids"), _dev(local_weights, "local_weights"),
+        _dev(work, "work"), ctypes.byref(lwork), _stream(stream)))
+
+
 def ShardFinalize(partial: torch.Tensor, n_samples: int, embed_width: int,
                   mode: CombineMode, offsets: Optional[torch.Tensor],
                   num_hots: int, sample0: int, weights: Optional[torch.Tensor],

@@ -179,8 +179,25 @@ int cuembed_shard_select(const void* indices, int idx_type, const void* offsets,
                          size_t* lwork, cuembed_stream_t stream) {
   return LaunchShardSelect(indices, idx_type, offsets, off_type, weights,
                            weight_dtype, batch_size, num_hots, row_lo, row_hi,
-                           local_offsets, local_indices, local_weights, work,
-                           lwork, reinterpret_cast<cudaStream_t>(stream));
+                           nullptr, local_offsets, local_indices, nullptr,
+                           local_weights, work, lwork,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_shard_select_coo(const void* indices, int idx_type,
+                             const void* offsets, int off_type,
+                             const void* weights, int weight_dtype,
+                             int batch_size, int num_hots, long long row_lo,
+                             long long row_hi, const int* counts,
+                             int* local_offsets, void* local_indices,
+                             void* local_sample_ids, void* local_weights,
+                             char* work, size_t* lwork,
+                             cuembed_stream_t stream) {
+  return LaunchShardSelect(indices, idx_type, offsets, off_type, weights,
+                           weight_dtype, batch_size, num_hots, row_lo, row_hi,
+                           counts, local_offsets, local_indices,
+                           local_sample_ids, local_weights, work, lwork,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cuembed_shard_finalize(const void* partial_f32, int n_samples,

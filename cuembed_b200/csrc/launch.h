@@ -48,8 +48,9 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
 int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
                       int off_type, const void* weights, int weight_dtype,
                       int batch_size, int num_hots, long long row_lo,
-                      long long row_hi, int* local_offsets,
-                      void* local_indices, void* local_weights, char* work,
+                      long long row_hi, const int* counts_in,
+                      int* local_offsets, void* local_indices,
+                      void* local_sample_ids, void* local_weights, char* work,
                       size_t* lwork, cudaStream_t stream);
 
 int LaunchShardFinalize(const void* partial_f32, int n_samples, int embed_width,

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kCtaThreads)
                     int batch, long long lo, long long hi,
                     const int* __restrict__ local_offsets,
                     IdxT* __restrict__ local_indices,
+                    IdxT* __restrict__ local_sample_ids,
                     void* __restrict__ local_weights) {
   using WT = typename std::conditional<WBYTES == 4, uint32_t, uint16_t>::type;
   const int lane = threadIdx.x & 31;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kCtaThreads)
       if (keep) {
         const int dst = out + __popc(m & lt);
         local_indices[dst] = static_cast<IdxT>(v - lo);
+        if (local_sample_ids != nullptr) local_sample_ids[dst] = static_cast<IdxT>(b);
         if constexpr (WBYTES != 0)
           static_cast<WT*>(local_weights)[dst] =
               static_cast<const WT*>(weights)[i];
@@ -190,8 +192,9 @@ int WarpGrid(int64_t warps) {
 int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
                       int off_type, const void* weights, int weight_dtype,
                       int batch_size, int num_hots, long long row_lo,
-                      long long row_hi, int* local_offsets,
-                      void* local_indices, void* local_weights, char* work,
+                      long long row_hi, const int* counts_in,
+                      int* local_offsets, void* local_indices,
+                      void* local_sample_ids, void* local_weights, char* work,
                       size_t* lwork, cudaStream_t stream) {
   if (lwork == nullptr || batch_size < 0) return CUEMBED_ERR_ARGUMENT;
   if (idx_type < 0 || idx_type > 1) return CUEMBED_ERR_DTYPE;
@@ -219,15 +222,18 @@ int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
   }
   if (indices == nullptr || local_indices == nullptr) return CUEMBED_ERR_ARGUMENT;
   if (weights != nullptr && local_weights == nullptr) return CUEMBED_ERR_ARGUMENT;
-  int* counts = reinterpret_cast<int*>(work + counts_off);
+  const int* counts = counts_in != nullptr
+                          ? counts_in
+                          : reinterpret_cast<int*>(work + counts_off);
   long long* sums = reinterpret_cast<long long*>(work + sums_off);
   const int off64 = off_type == CUEMBED_I64;
   const int grid = WarpGrid(batch_size);
   const int wbytes = weights != nullptr ? static_cast<int>(ElemSize(weight_dtype)) : 0;
 #define SELECT(IdxT)                                                            \
-  ShardCountKernel<IdxT><<<grid, kCtaThreads, 0, stream>>>(                     \
-      static_cast<const IdxT*>(indices), offsets, off64, num_hots, batch_size,  \
-      row_lo, row_hi, counts);                                                  \
+  if (counts_in == nullptr)                                                     \
+    ShardCountKernel<IdxT><<<grid, kCtaThreads, 0, stream>>>(                   \
+        static_cast<const IdxT*>(indices), offsets, off64, num_hots,            \
+        batch_size, row_lo, row_hi, reinterpret_cast<int*>(work + counts_off)); \
   ScanPartSumKernel<<<parts, kCtaThreads, 0, stream>>>(counts, batch_size,      \
                                                        chunks_per_part, sums);  \
   ScanWriteKernel<<<parts, kCtaThreads, 0, stream>>>(                           \
@@ -236,24 +242,27 @@ int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
     ShardFillKernel<IdxT, 0><<<grid, kCtaThreads, 0, stream>>>(                 \
         static_cast<const IdxT*>(indices), offsets, off64, num_hots, weights,   \
         batch_size, row_lo, row_hi, local_offsets,                              \
-        static_cast<IdxT*>(local_indices), local_weights);                      \
+        static_cast<IdxT*>(local_indices),                                      \
+        static_cast<IdxT*>(local_sample_ids), local_weights);                   \
   else if (wbytes == 2)                                                         \
     ShardFillKernel<IdxT, 2><<<grid, kCtaThreads, 0, stream>>>(                 \
         static_cast<const IdxT*>(indices), offsets, off64, num_hots, weights,   \
         batch_size, row_lo, row_hi, local_offsets,                              \
-        static_cast<IdxT*>(local_indices), local_weights);                      \
+        static_cast<IdxT*>(local_indices),                                      \
+        static_cast<IdxT*>(local_sample_ids), local_weights);                   \
   else                                                                          \
     ShardFillKernel<IdxT, 4><<<grid, kCtaThreads, 0, stream>>>(                 \
         static_cast<const IdxT*>(indices), offsets, off64, num_hots, weights,   \
         batch_size, row_lo, row_hi, local_offsets,                              \
-        static_cast<IdxT*>(local_indices), local_weights)
+        static_cast<IdxT*>(local_indices),                                      \
+        static_cast<IdxT*>(local_sample_ids), local_weights)
   if (idx_type == CUEMBED_I64) {
     SELECT(int64_t);
   } else {
     SELECT(int32_t);
   }
 #undef SELECT
-  CountLaunch(4);
+  CountLaunch(counts_in == nullptr ? 4 : 3);
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
 

@@ -15,8 +15,8 @@
 //             [this rank][bag - owner * per] of the rank that owns the bag.
 //             The NVLink transfer therefore overlaps the gather bag by bag, and
 //             there is neither a local partial buffer nor a select pass.
-//             Ranks start at different owners so that no receiver is hit by
-//             all senders at once.
+//             Consecutive bags belong to consecutive owners (starting at
+//             rank + 1), so pushes are spread over the kernel and the receivers.
 //   signal    one release-store per peer (after the kernel boundary, which
 //             makes the pushes visible system-wide).
 //   finalize  ShardReduceFinalizeKernel: waits (acquire loads) for the flag of
@@ -114,7 +114,8 @@ struct PushArgs {
   long long lo, hi;
   int batch;
   int per;  // bags per owner
-  int first_bag;
+  int rank;
+  int world;
   int num_hots;
   int off64;
   int out_dt;
@@ -164,10 +165,12 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
   for (int seq0 = warp_first; seq0 < a.batch; seq0 += total_groups) {
     const int seq = seq0 + gw;
     const bool bag_ok = seq < a.batch;
-    // Rank r starts with the bags of owner r + 1: senders never gang up on one
-    // receiver, and the rank's own bags (no NVLink) come last.
-    int bag = seq + a.first_bag;
-    if (bag >= a.batch) bag -= a.batch;
+    // Consecutive bags go to consecutive owners, starting at rank + 1: the
+    // NVLink pushes are spread evenly over the whole kernel (they overlap the
+    // bags pooled for the rank itself) and over the receivers.
+    int owner = a.rank + 1 + seq % a.world;
+    if (owner >= a.world) owner -= a.world;
+    const int bag = owner * a.per + seq / a.world;
     int64_t start = 0;
     int len = 0;
     if (bag_ok) {
@@ -250,7 +253,6 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
     }
 
     if (bag_ok) {
-      const int owner = bag / a.per;
       if (active) {
         char* dst = static_cast<char*>(a.slots.p[owner]) +
                     static_cast<int64_t>(bag - owner * a.per) * a.out_row_bytes;
@@ -650,7 +652,8 @@ int cuembed_shard_pool_push(const void* local_params, int in_dtype,
   a.hi = row_hi;
   a.batch = batch_size;
   a.per = batch_size / world;
-  a.first_bag = ((rank + 1) % world) * a.per;
+  a.rank = rank;
+  a.world = world;
   a.num_hots = num_hots;
   a.off64 = off_type == CUEMBED_I64;
   a.out_dt = partial_dtype;

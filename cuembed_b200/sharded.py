@@ -77,6 +77,26 @@ class CudaLocalOps:
                         local_offsets, local_indices, local_weights, work)
         return local_offsets, local_indices, local_weights
 
+    def shard_select_coo(self, indices, offsets, weights, batch, num_hots, lo, hi,
+                         counts=None, nnz_cap=None):
+        """Selection in COO form: (local_offsets, local_indices, sample_ids,
+        local_weights); `counts` from the pooling kernel saves the counting pass,
+        `nnz_cap` (the number of owned lookups, if known) sizes the outputs."""
+        api = self.api
+        dev = indices.device
+        cap = indices.numel() if nnz_cap is None else nnz_cap
+        local_offsets = torch.empty(batch + 1, dtype=torch.int32, device=dev)
+        local_indices = torch.empty(max(cap, 1), dtype=indices.dtype, device=dev)
+        sample_ids = torch.empty(max(cap, 1), dtype=indices.dtype, device=dev)
+        local_weights = torch.empty(max(cap, 1), dtype=weights.dtype, device=dev) \
+            if weights is not None else None
+        nbytes = api.ShardSelect(indices, offsets, weights, batch, num_hots, lo, hi,
+                                 None, None, None, None)
+        work = self._scratch("select", nbytes, dev)
+        api.ShardSelectCoo(indices, offsets, weights, batch, num_hots, lo, hi, counts,
+                           local_offsets, local_indices, sample_ids, local_weights, work)
+        return local_offsets, local_indices, sample_ids, local_weights
+
     def pool_partial(self, table, local_indices, local_offsets, local_weights, batch):
         width = table.shape[1]
         partial = torch.empty(batch, width, dtype=torch.float32, device=table.device)
@@ -136,8 +156,9 @@ class CudaLocalOps:
                 inv = torch.empty(rows, dtype=t_idx.dtype, device=dev)
             grad = torch.empty(rows, width, dtype=grad_y.dtype, device=dev)
         rows = grad.shape[0]
+        # every row of a compressed gradient is written: no zero-fill needed
         api.EmbeddingBackward(grad_y, width, rows, local_nnz, t_idx, t_sid, remapped,
-                              t_w, False, grad, inv)
+                              t_w, remapped is not None, grad, inv)
         return grad, inv
 
     def local_backward(self, grad_y, local_offsets, local_indices, local_weights,

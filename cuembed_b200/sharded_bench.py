@@ -154,6 +154,18 @@ def run_p2p(args, rank, local_rank, world):
         one_step()
     torch.cuda.synchronize()
     dist.barrier()
+    if getattr(args, "trace", None):
+        # CUPTI timeline of a few steps (not a bench number): per-kernel GPU time
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                one_step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            with open(args.trace, "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60,
+                                                  max_name_column_width=90))
+        dist.barrier()
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

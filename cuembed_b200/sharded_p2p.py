@@ -228,13 +228,14 @@ class PeerShardedEmbedding:
                 raise CuEmbedError("sharded concat backward needs nnz < 2^31")
             weights = torch.arange(ctx.indices.numel(), dtype=torch.int32,
                                    device=self.device).view(torch.float32)
-        l_off, l_idx, l_w = self.ops.shard_select(ctx.indices, ctx.offsets, weights,
-                                                  ctx.batch, ctx.num_hots, self.lo, self.hi)
+        l_off, l_idx, l_sid, l_w = self.ops.shard_select_coo(
+            ctx.indices, ctx.offsets, weights, ctx.batch, ctx.num_hots, self.lo, self.hi,
+            counts=ctx.counts, nnz_cap=local_nnz)
         ctx.local_nnz = int(l_off[-1].item()) if local_nnz is None else int(local_nnz)
         if ctx.local_nnz == 0:
             ctx.coo = ()
             return
-        sample_ids = None
+        sample_ids = l_sid[:ctx.local_nnz]
         if concat:
             sample_ids = l_w[:ctx.local_nnz].view(torch.int32).to(l_idx.dtype)
             l_w = None

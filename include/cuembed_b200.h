@@ -170,6 +170,24 @@ int cuembed_shard_select(const void* indices, int idx_type, const void* offsets,
                          size_t* lwork, cuembed_stream_t stream);
 
 /*
+ * The same selection producing the COO form the transpose consumes directly:
+ * local_sample_ids (optional, same integer type as indices) receives the bag of
+ * every selected lookup, so no row-id extraction pass is needed; counts
+ * (optional, [batch_size] int32, e.g. from cuembed_shard_pool_push) are the
+ * per-bag numbers of selected lookups if the caller already has them, which
+ * saves the counting pass over the indices.
+ */
+int cuembed_shard_select_coo(const void* indices, int idx_type,
+                             const void* offsets, int off_type,
+                             const void* weights, int weight_dtype,
+                             int batch_size, int num_hots, long long row_lo,
+                             long long row_hi, const int* counts,
+                             int* local_offsets, void* local_indices,
+                             void* local_sample_ids, void* local_weights,
+                             char* work, size_t* lwork,
+                             cuembed_stream_t stream);
+
+/*
  * Epilogue after the reduce-scatter of the fp32 partial sums: for the samples
  * [sample0, sample0 + n_samples) of the global batch, out = partial (sum) or
  * partial / global bag length (mean; / sum of weights if weights != NULL, zero
