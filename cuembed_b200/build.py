@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-Xcompiler", "-fPIC",
+    # tuning experiments only, e.g. CUEMBED_NVCC_EXTRA="-DBWD_MINB=6"
+    *os.environ.get("CUEMBED_NVCC_EXTRA", "").split(),
 ]
 
 

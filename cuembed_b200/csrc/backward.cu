@@ -12,10 +12,14 @@
 //     accumulating weight * grad_y[sample] in fp32 registers, with UNROLL row
 //     loads in flight;
 //   * a run of equal rows that lies inside one chunk is rounded once and
-//     stored directly; a run that crosses chunk edges leaves a head / tail
-//     partial in shared memory, and the CTA stitches its chunks in chunk order;
-//   * runs that cross CTA edges leave one head and one tail partial per CTA in
-//     a small fp32 scratch; a second kernel adds them in CTA order.
+//     stored directly; a run that crosses chunk edges leaves one head and / or
+//     one tail partial per chunk in an fp32 scratch (written only then);
+//     lane groups never wait for each other -- no shared memory, no barrier
+//     (the first version stitched the chunks of a CTA through shared memory
+//     and lost a quarter of its warp time at that barrier: cold rows cost a
+//     load and a store per nonzero, hot runs only a load);
+//   * a second kernel adds, in chunk order, tail + following heads of every
+//     run that crosses chunk edges.
 //   Every sum therefore has a fixed association order: results are identical
 //   from run to run, with one rounding to the gradient type per element.
 //   * inverse_mapping (compressed gradients) is written where each run ends,
@@ -37,18 +41,19 @@ struct BwdArgs {
   const void* weights;
   void* grad;
   void* inverse_mapping;
-  float* scratch;       // [num_ctas][2][width]
-  int* meta;            // [num_ctas][2] : head kind, has tail
-  long long* meta_row;  // [num_ctas][2] : head row, tail row
+  float* scratch;       // [num_chunks][2][width]: head partial, tail partial
+  int* meta;            // [num_chunks][2] : head kind, has tail
+  long long* meta_row;  // [num_chunks][2] : head row, tail row
   int64_t row_bytes;
   int width;
   int nnz;
   int nvec;
   int lanes;
   int log2_lanes;
-  int rounds;  // rounds of G nonzeros per lane group (K = G * rounds)
-  int cta_nz;  // nonzeros per CTA = 256 * rounds
+  int rounds;      // rounds of G nonzeros per lane group (K = G * rounds)
+  int cta_nz;      // nonzeros per CTA = kBwdThreads * rounds
   int num_ctas;
+  int num_chunks;  // = num_ctas * lane groups per CTA
 };
 
 constexpr int kHeadNone = 0;
@@ -80,24 +85,46 @@ __device__ __forceinline__ void StoreOneAs<__nv_bfloat16>(__nv_bfloat16* p,
   *p = __float2bfloat16_rn(v);
 }
 
+constexpr int kBwdThreads = 128;
+#ifndef BWD_MINB
+#define BWD_MINB 7
+#endif
+
+template <int NE>
+__device__ __forceinline__ void StorePartial(float* dst, const float* acc) {
+  if constexpr (NE % 4 == 0) {
+#pragma unroll
+    for (int e = 0; e < NE; e += 4)
+      *reinterpret_cast<float4*>(dst + e) =
+          make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+  } else if constexpr (NE % 2 == 0) {
+#pragma unroll
+    for (int e = 0; e < NE; e += 2)
+      *reinterpret_cast<float2*>(dst + e) = make_float2(acc[e], acc[e + 1]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) dst[e] = acc[e];
+  }
+}
+
 template <typename T, int V, typename IdxT, bool WEIGHTED, int UNROLL>
-__global__ void __launch_bounds__(kCtaThreads, 3)
+__global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     BwdSegReduceKernel(const BwdArgs a) {
   using VecT = typename VecBits<V>::type;
   constexpr int NW = V / 4;
   constexpr int NE = NW * Elem<T>::kPerWord;
   constexpr unsigned kFull = 0xffffffffu;
 
-  __shared__ float s_part[2][kCtaThreads * NE];
-  __shared__ long long s_row[2][kCtaThreads];
-  __shared__ int s_kind[kCtaThreads];
-  __shared__ int s_tail[kCtaThreads];
-
   const int tid = threadIdx.x;
   const int G = a.lanes;
   const int lane_g = tid & (G - 1);
   const int g = tid >> a.log2_lanes;
-  const int groups_per_cta = kCtaThreads >> a.log2_lanes;
+  const int groups_per_cta = kBwdThreads >> a.log2_lanes;
+  const int chunk = blockIdx.x * groups_per_cta + g;
+  float* __restrict__ my_head =
+      a.scratch + (static_cast<size_t>(chunk) * 2 + 0) * a.width;
+  float* __restrict__ my_tail =
+      a.scratch + (static_cast<size_t>(chunk) * 2 + 1) * a.width;
   const int gl0 = (tid & 31) & ~(G - 1);  // first lane of this group in the warp
   // One bit per lane group of the warp (bit k*G), to test "does any group end
   // a run at position j" with a warp-uniform branch.
@@ -214,9 +241,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
             krow = __shfl_sync(kFull, key, j, G);
           if (((endsw >> (gl0 + j)) & 1u) != 0u) {
             if (in_first && cont) {
-              // Run began in an earlier chunk: partial, stitched below.
-#pragma unroll
-              for (int e = 0; e < NE; ++e) s_part[0][tid * NE + e] = acc[e];
+              // Run began in an earlier chunk: partial, added by the fix-up.
+              if (active) StorePartial<NE>(my_head + v * NE, acc);
               head_kind = kHeadEnds;
               head_row = krow;
             } else if (active) {
@@ -246,138 +272,68 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
   if (open) {
     if (in_first && cont) {
       head_kind = kHeadThrough;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) s_part[0][tid * NE + e] = acc[e];
+      if (active) StorePartial<NE>(my_head + v * NE, acc);
     } else {
       has_tail = 1;
       tail_row = __ldg(keys + c0 + n_g - 1);
-#pragma unroll
-      for (int e = 0; e < NE; ++e) s_part[1][tid * NE + e] = acc[e];
+      if (active) StorePartial<NE>(my_tail + v * NE, acc);
     }
   }
-  if (lane_g == 0) {
-    s_kind[g] = head_kind;
-    s_tail[g] = has_tail;
-    s_row[0][g] = static_cast<long long>(head_row);
-    s_row[1][g] = static_cast<long long>(tail_row);
-  }
-  __syncthreads();
-
-  // ---- stitch the chunks of this CTA in chunk order (one thread per column
-  //      of the row tile); what crosses the CTA edge goes to the scratch.
-  const int tile_cols = G * NE;
-  if (tid < tile_cols) {
-    const int col = blockIdx.y * tile_cols + tid;
-    const bool col_ok = col < a.width;
-    float* scratch_head =
-        a.scratch + (static_cast<size_t>(blockIdx.x) * 2 + 0) * a.width;
-    float* scratch_tail =
-        a.scratch + (static_cast<size_t>(blockIdx.x) * 2 + 1) * a.width;
-    T* grad = static_cast<T*>(a.grad);
-    float carry = 0.f;
-    bool carry_valid = false, origin_before = false;
-    long long carry_row = 0;
-    int cta_head_kind = kHeadNone, cta_has_tail = 0;
-    long long cta_head_row = 0, cta_tail_row = 0;
-    for (int q = 0; q < groups_per_cta; ++q) {
-      const int hk = s_kind[q];
-      if (hk == kHeadThrough) {
-        if (!carry_valid) {
-          carry = 0.f;
-          carry_valid = true;
-          origin_before = true;
-        }
-        carry = __fadd_rn(carry, s_part[0][q * tile_cols + tid]);
-      } else {
-        if (hk == kHeadEnds) {
-          if (!carry_valid) {
-            carry = 0.f;
-            origin_before = true;
-          }
-          const float total = __fadd_rn(carry, s_part[0][q * tile_cols + tid]);
-          if (origin_before) {
-            if (col_ok) scratch_head[col] = total;
-            cta_head_kind = kHeadEnds;
-            cta_head_row = s_row[0][q];
-          } else if (col_ok) {
-            StoreOneAs<T>(grad + s_row[0][q] * a.width + col, total);
-          }
-          carry_valid = false;
-          origin_before = false;
-        }
-        if (s_tail[q] != 0) {
-          carry = s_part[1][q * tile_cols + tid];
-          carry_valid = true;
-          origin_before = false;
-          carry_row = s_row[1][q];
-        }
-      }
-    }
-    if (carry_valid) {
-      if (origin_before) {
-        cta_head_kind = kHeadThrough;
-        if (col_ok) scratch_head[col] = carry;
-      } else {
-        cta_has_tail = 1;
-        cta_tail_row = carry_row;
-        if (col_ok) scratch_tail[col] = carry;
-      }
-    }
-    if (tid == 0) {
-      a.meta[blockIdx.x * 2 + 0] = cta_head_kind;
-      a.meta[blockIdx.x * 2 + 1] = cta_has_tail;
-      a.meta_row[blockIdx.x * 2 + 0] = cta_head_row;
-      a.meta_row[blockIdx.x * 2 + 1] = cta_tail_row;
-    }
+  if (lane_g == 0 && blockIdx.y == 0) {
+    a.meta[chunk * 2 + 0] = head_kind;
+    a.meta[chunk * 2 + 1] = has_tail;
+    a.meta_row[chunk * 2 + 0] = static_cast<long long>(head_row);
+    a.meta_row[chunk * 2 + 1] = static_cast<long long>(tail_row);
   }
 }
 
-// Adds, in CTA order, the partials of every run that crosses CTA edges:
-// tail of the CTA where the run starts + heads of the following CTAs.  The
+// Adds, in chunk order, the partials of every run that crosses chunk edges:
+// tail of the chunk where the run starts + heads of the following chunks.  The
 // chain length is found first (all threads scan the head kinds), so the loads
-// of the partial rows are independent and issued eight at a time.
+// of the partial rows are independent and issued sixteen at a time.
 template <typename T>
 __global__ void __launch_bounds__(kCtaThreads)
     BwdFixupKernel(const BwdArgs a) {
   __shared__ int s_len;
-  const int cta = blockIdx.x;
-  if (a.meta[cta * 2 + 1] == 0) return;
+  const int c0 = blockIdx.x;
+  if (a.meta[c0 * 2 + 1] == 0) return;
   const int tid = threadIdx.x;
-  // chain = CTAs cta+1 .. cta+len; the last one has kind "ends".
+  // chain = chunks c0+1 .. c0+len; the last one has kind "ends".
   if (tid == 0) s_len = 0x7fffffff;
   __syncthreads();
-  for (int base = cta + 1; base < a.num_ctas; base += kCtaThreads) {
+  for (int base = c0 + 1; base < a.num_chunks; base += kCtaThreads) {
     const int c = base + tid;
-    if (c < a.num_ctas && a.meta[c * 2 + 0] != kHeadThrough)
-      atomicMin(&s_len, c - cta);
+    if (c < a.num_chunks && a.meta[c * 2 + 0] != kHeadThrough)
+      atomicMin(&s_len, c - c0);
     __syncthreads();
     if (s_len != 0x7fffffff) break;
   }
   __syncthreads();
   int len = s_len;
-  if (len == 0x7fffffff) len = a.num_ctas - 1 - cta;  // malformed input guard
+  if (len == 0x7fffffff) len = a.num_chunks - 1 - c0;  // malformed input guard
   // a "none" head at the end of the chain means the run ended exactly at the
-  // CTA edge (cannot happen for a tail, kept as a guard): exclude it.
-  if (cta + len < a.num_ctas && a.meta[(cta + len) * 2 + 0] == kHeadNone) --len;
+  // chunk edge (cannot happen for a tail, kept as a guard): exclude it.
+  if (c0 + len < a.num_chunks && a.meta[(c0 + len) * 2 + 0] == kHeadNone) --len;
 
   const int col = blockIdx.y * kCtaThreads + tid;
   if (col >= a.width) return;
   const float* scratch = a.scratch;
   const size_t pitch = static_cast<size_t>(2) * a.width;
-  float acc = scratch[static_cast<size_t>(cta) * pitch + a.width + col];
-  int c = cta + 1;
-  const int end = cta + len;  // inclusive
-  for (; c + 7 <= end; c += 8) {
-    float v[8];
+  float acc = scratch[static_cast<size_t>(c0) * pitch + a.width + col];
+  int c = c0 + 1;
+  const int end = c0 + len;  // inclusive
+  constexpr int kInFlight = 16;
+  for (; c + kInFlight - 1 <= end; c += kInFlight) {
+    float v[kInFlight];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < kInFlight; ++u)
       v[u] = scratch[static_cast<size_t>(c + u) * pitch + col];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
+    for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
   }
   for (; c <= end; ++c)
     acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
-  const long long row = a.meta_row[cta * 2 + 1];
+  const long long row = a.meta_row[c0 * 2 + 1];
   StoreOneAs<T>(static_cast<T*>(a.grad) + row * a.width + col, acc);
 }
 
@@ -393,10 +349,11 @@ struct BwdLayout {
   int rounds;
   int cta_nz;
   int num_ctas;
+  int num_chunks;
   size_t scratch_off, meta_off, row_off, total;
 };
 
-BwdLayout MakeBwdLayout(int nnz, int embed_width) {
+BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
   BwdLayout L;
   static const int rounds_env = EnvInt("CUEMBED_BWD_ROUNDS", 0);
   int rounds = rounds_env;
@@ -410,16 +367,17 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width) {
       rounds *= 2;
   }
   L.rounds = rounds;
-  L.cta_nz = rounds * kCtaThreads;
+  L.cta_nz = rounds * kBwdThreads;
   L.num_ctas = nnz > 0 ? (nnz + L.cta_nz - 1) / L.cta_nz : 0;
+  L.num_chunks = L.num_ctas * (kBwdThreads / lanes);
   size_t off = 0;
   L.scratch_off = off;
-  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * embed_width * sizeof(float),
+  off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * embed_width * sizeof(float),
                  256);
   L.meta_off = off;
-  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * sizeof(int), 256);
+  off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(int), 256);
   L.row_off = off;
-  off += AlignUp(static_cast<size_t>(L.num_ctas) * 2 * sizeof(long long), 256);
+  off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(long long), 256);
   L.total = off > 0 ? off : 256;
   return L;
 }
@@ -430,11 +388,11 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   dim3 grid(a.num_ctas, col_tiles);
   if (unroll == 4)
     BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4>
-        <<<grid, kCtaThreads, 0, stream>>>(a);
+        <<<grid, kBwdThreads, 0, stream>>>(a);
   else
     BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8>
-        <<<grid, kCtaThreads, 0, stream>>>(a);
-  dim3 fgrid(a.num_ctas, (a.width + kCtaThreads - 1) / kCtaThreads);
+        <<<grid, kBwdThreads, 0, stream>>>(a);
+  dim3 fgrid(a.num_chunks, (a.width + kCtaThreads - 1) / kCtaThreads);
   BwdFixupKernel<T><<<fgrid, kCtaThreads, 0, stream>>>(a);
   CountLaunch(2);
 }
@@ -483,7 +441,11 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
     return CUEMBED_ERR_DTYPE;
   const int64_t row_bytes = static_cast<int64_t>(embed_width) * ElemSize(dtype);
   if (row_bytes % 4 != 0) return CUEMBED_ERR_ROW_BYTES;
-  const BwdLayout L = MakeBwdLayout(nnz, embed_width);
+  // Scratch is sized for the aligned case (fewest lanes per row = most chunks);
+  // a misaligned call uses narrower vectors, i.e. fewer, wider lane groups.
+  RowShape shape;
+  MakeRowShape(embed_width, dtype, &shape);
+  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes);
   if (work == nullptr) {
     *lwork = L.total;
     return CUEMBED_OK;
@@ -509,8 +471,6 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
   if ((reinterpret_cast<uintptr_t>(work) & 15) != 0)
     return CUEMBED_ERR_ARGUMENT;
 
-  RowShape shape;
-  MakeRowShape(embed_width, dtype, &shape);
   // Vector width limited by the actual pointer alignment.
   int v = shape.vec_bytes;
   const uint64_t bits = reinterpret_cast<uint64_t>(grad_y) |
@@ -541,6 +501,7 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
   a.rounds = L.rounds;
   a.cta_nz = L.cta_nz;
   a.num_ctas = L.num_ctas;
+  a.num_chunks = L.num_ctas * (kBwdThreads / a.lanes);
   const int col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
   const bool weighted = transpose_weights != nullptr;
 
