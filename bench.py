@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE.json configs[0] (CPU reference check shape)
     "C1": dict(num_categories=1_048_576, embed_width=32, batch_size=1024,
                hotness=8, alpha=0.0, dtype="f32", index="int32"),
+    # BASELINE.json configs[4]: ONE table sharded by rows over the ranks (strong
+    # scaling: the global problem is fixed; N > 1 only)
+    "C5": dict(num_categories=400_000_000, embed_width=128, batch_size=262144,
+               hotness=64, alpha=1.15, dtype="f16", index="int32", global_problem=True),
     # small shape for smoke runs
     "tiny": dict(num_categories=100_000, embed_width=256, batch_size=4096,
                  hotness=64, alpha=1.15, dtype="f16", index="int32"),

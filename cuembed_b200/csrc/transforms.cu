@@ -349,8 +349,12 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
   __shared__ int32_t s_goff[kRadix];        // global start - tile start
   __shared__ uint32_t s_scan[kWarpsPerCta];
   __shared__ int s_tile;
+  // Keys and sample ids travel through shared memory together, as pairs.
+  struct alignas(2 * sizeof(KeyT)) Pair {
+    KeyT k, v;
+  };
   extern __shared__ __align__(16) unsigned char s_exch_raw[];
-  KeyT* s_exch = reinterpret_cast<KeyT*>(s_exch_raw);
+  Pair* s_exch = reinterpret_cast<Pair*>(s_exch_raw);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -407,27 +411,40 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
                  (static_cast<size_t>(a.pass) * a.num_tiles) * kRadix + tid;
   const int warp_base = warp * (32 * ITEMS);
 
+  // The id of the next tile is fetched while the current tile is processed
+  // (the atomic's round trip is off the critical path).
+  int next_tile = 0;
+  if (tid == 0)
+    next_tile = static_cast<int>(atomicAdd(&a.tile_counters[a.pass], 1u));
   while (true) {
     __syncthreads();  // previous tile done with the shared arrays
-    if (tid == 0)
-      s_tile = static_cast<int>(atomicAdd(&a.tile_counters[a.pass], 1u));
+    if (tid == 0) s_tile = next_tile;
     for (int i = tid; i < kWarpsPerCta * kRadix; i += kCtaThreads)
       (&s_warp_cnt[0][0])[i] = 0;
     __syncthreads();
     const int tile = s_tile;
     if (tile >= a.num_tiles) break;
+    if (tid == 0)
+      next_tile = static_cast<int>(atomicAdd(&a.tile_counters[a.pass], 1u));
     const int tile_base = tile * TILE;
     const int tile_n = min(TILE, a.nnz - tile_base);
 
-    // ---- load keys (payload is loaded after the keys have been scattered: a
-    // software-pipelined variant that prefetched the next tile was measured
+    // ---- load keys and sample ids together: the payload's load latency
+    // hides behind the ranking instead of following the key exchange.  (A
+    // software-pipelined variant that prefetched the NEXT tile was measured
     // slower because it delays the publication of the tile's digit counts,
-    // profiles/r01_notes.md)
+    // profiles/r01_notes.md.)
     KeyT key[ITEMS];
+    KeyT val[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       const int local = warp_base + i * 32 + lane;
       key[i] = local < tile_n ? kin[tile_base + local] : KeyT(0);
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int local = warp_base + i * 32 + lane;
+      val[i] = local < tile_n ? vin[tile_base + local] : KeyT(0);
     }
 
     // ---- stable ranking inside the warp.  Items are warp-striped so that
@@ -479,16 +496,34 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
     }
     if (lane == 31) s_scan[warp] = tscan;
 
+    // Decoupled look-back, kLookWin predecessors per round: their status words
+    // are loaded together (independent loads, one L2 round trip) and consumed
+    // in order.  The serial one-hop-per-round-trip walk was the top stall of
+    // the pass (19 hops per tile on average, half of all warp samples,
+    // profiles/r01_notes.md).
     uint32_t exclusive = 0;
     if (tile > 0 && a.debug != 1) {
+      constexpr int kLookWin = 8;
       int prev = tile - 1;
-      while (true) {
-        uint32_t s = LdVolatile(&lb[static_cast<size_t>(prev) * kRadix]);
-        while ((s & ~kValueMask) == 0)
-          s = LdVolatile(&lb[static_cast<size_t>(prev) * kRadix]);
-        exclusive += s & kValueMask;
-        if ((s & kFlagPrefix) != 0) break;
-        --prev;
+      bool done = false;
+      while (!done) {
+        uint32_t st[kLookWin];
+#pragma unroll
+        for (int u = 0; u < kLookWin; ++u) {
+          const int p = prev - u;
+          st[u] = LdVolatile(&lb[static_cast<size_t>(p < 0 ? 0 : p) * kRadix]);
+        }
+#pragma unroll
+        for (int u = 0; u < kLookWin; ++u) {
+          if (!done) {
+            uint32_t sw = st[u];
+            while ((sw & ~kValueMask) == 0)
+              sw = LdVolatile(&lb[static_cast<size_t>(prev - u) * kRadix]);
+            exclusive += sw & kValueMask;
+            if ((sw & kFlagPrefix) != 0) done = true;
+          }
+        }
+        prev -= kLookWin;
       }
       StVolatile(&lb[static_cast<size_t>(tile) * kRadix],
                  kFlagPrefix | (exclusive + tile_count));
@@ -504,7 +539,7 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
                   static_cast<int32_t>(t_excl);
     __syncthreads();
 
-    // ---- final position of every item inside the tile; keys through smem
+    // ---- final position of every item inside the tile; pairs through smem
     uint32_t pos[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -512,7 +547,10 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
       if (local < tile_n) {
         const uint32_t d = DigitOf<KeyT>(key[i], a.pass);
         pos[i] = s_tile_excl[d] + s_warp_cnt[warp][d] + rank[i];
-        s_exch[pos[i]] = key[i];
+        Pair pr;
+        pr.k = key[i];
+        pr.v = val[i];
+        s_exch[pos[i]] = pr;
       } else {
         pos[i] = 0;
       }
@@ -523,26 +561,13 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
     for (int i = 0; i < ITEMS; ++i) {
       const int p = tid + i * kCtaThreads;
       if (p < tile_n) {
-        const KeyT k = s_exch[p];
-        gaddr[i] = s_goff[DigitOf<KeyT>(k, a.pass)] + p;
-        kout[gaddr[i]] = k;
+        const Pair pr = s_exch[p];
+        gaddr[i] = s_goff[DigitOf<KeyT>(pr.k, a.pass)] + p;
+        kout[gaddr[i]] = pr.k;
+        vout[gaddr[i]] = pr.v;
       } else {
         gaddr[i] = -1;
       }
-    }
-    __syncthreads();
-
-    // ---- payload: sample ids (same type as keys) through the same buffer
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int local = warp_base + i * 32 + lane;
-      if (local < tile_n) s_exch[pos[i]] = vin[tile_base + local];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int p = tid + i * kCtaThreads;
-      if (p < tile_n) vout[gaddr[i]] = s_exch[p];
     }
 
     // ---- payload: weights
@@ -609,7 +634,7 @@ SortLayout MakeSortLayout(int nnz, int idx_type, int wbytes) {
 template <typename KeyT, int WBYTES, int ITEMS>
 void LaunchPasses(const SortArgs& base, cudaStream_t stream) {
   constexpr int ND = sizeof(KeyT);
-  const size_t smem = static_cast<size_t>(ITEMS) * kCtaThreads * sizeof(KeyT);
+  const size_t smem = static_cast<size_t>(ITEMS) * kCtaThreads * 2 * sizeof(KeyT);
   auto kernel = RadixPassKernel<KeyT, WBYTES, ITEMS>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {

@@ -82,8 +82,10 @@ def make_inputs(args, rank, world, dev):
     tdt = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[cfg["dtype"]]
     idt = torch.int32 if cfg["index"] == "int32" else torch.int64
     shard_rows, w, hot = cfg["num_categories"], cfg["embed_width"], cfg["hotness"]
-    rows = shard_rows * world
-    batch = cfg["batch_size"] * world
+    if cfg.get("global_problem"):
+        rows, batch = cfg["num_categories"], cfg["batch_size"]      # strong scaling
+    else:
+        rows, batch = shard_rows * world, cfg["batch_size"] * world  # weak scaling
     nnz = batch * hot
     lo, hi = row_range(rows, world, rank)
     indices = torch.empty(nnz, dtype=idt, device=dev)
@@ -95,9 +97,8 @@ def make_inputs(args, rank, world, dev):
     g = torch.Generator(device=dev)
     g.manual_seed(123456 + rank)
     table = torch.empty(hi - lo, w, dtype=tdt, device=dev)
-    for r0 in range(0, hi - lo, 1 << 20):
-        r1 = min(hi - lo, r0 + (1 << 20))
-        table[r0:r1] = (torch.rand(r1 - r0, w, generator=g, device=dev) * 2 - 1).to(tdt)
+    for r0 in range(0, hi - lo, 1 << 24):  # U(-1, 1) in place, 16 Mi rows at a time
+        table[r0:min(hi - lo, r0 + (1 << 24))].uniform_(-1.0, 1.0, generator=g)
     per = batch // world
     g.manual_seed(654321 + rank)
     grad_slice = torch.randint(-10, 11, (per, w), generator=g, device=dev).to(tdt)
@@ -246,10 +247,11 @@ def run_p2p(args, rank, local_rank, world):
             "value": round(nnz / (ms_per_step * 1e-3), 1), "unit": "lookups/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "scaling": "strong" if cfg.get("global_problem") else "weak",
+            "vs_baseline": None, "dtype": cfg["dtype"],
             "data": "synthetic",
-            "config": {"workload": f"row-sharded manual_benchmark shape: {world} shards of "
-                                   f"{shard_rows}x{w} {cfg['dtype']} (global {rows} rows), global batch "
+            "config": {"workload": f"row-sharded {args.workload}: {world} shards of "
+                                   f"{table.shape[0]}x{w} {cfg['dtype']} (global {rows} rows), global batch "
                                    f"{batch}, hotness {hot}, alpha {cfg['alpha']}, {cfg['index']} indices, "
                                    f"sum, compressed grad",
                        "parallelism": f"row-sharded x{world}, exchange fused over NVLink peer memory: "
