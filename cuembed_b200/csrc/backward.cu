@@ -42,6 +42,7 @@ struct BwdArgs {
   void* grad;
   void* inverse_mapping;
   float* scratch;       // [num_chunks][2][width]: head partial, tail partial
+  float* group_part;    // [num_chunks / kFixGroup][width]: sums of through groups
   int* meta;            // [num_chunks][2] : head kind, has tail
   long long* meta_row;  // [num_chunks][2] : head row, tail row
   int64_t row_bytes;
@@ -287,10 +288,49 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
   }
 }
 
-// Adds, in chunk order, the partials of every run that crosses chunk edges:
-// tail of the chunk where the run starts + heads of the following chunks.  The
-// chain length is found first (all threads scan the head kinds), so the loads
-// of the partial rows are independent and issued sixteen at a time.
+// Fix-up, level 1: a GROUP of kFixGroup consecutive chunks that all lie inside
+// one long run ("through" chunks) is summed, in chunk order, into one partial
+// row.  Only the interiors of very hot rows produce such groups; they make the
+// chains of level 2 up to kFixGroup times shorter (a 262144-sample batch puts
+// the hottest row into 2048 consecutive chunks).
+constexpr int kFixGroup = 32;
+
+__global__ void __launch_bounds__(kCtaThreads)
+    BwdGroupKernel(const BwdArgs a) {
+  __shared__ int s_all;
+  const int g = blockIdx.x;
+  const int c_first = g * kFixGroup;
+  if (c_first + kFixGroup > a.num_chunks) return;
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    const bool through = a.meta[(c_first + tid) * 2 + 0] == kHeadThrough;
+    const bool all = __all_sync(0xffffffffu, through);
+    if (tid == 0) s_all = all ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_all == 0) return;
+  const int col = blockIdx.y * kCtaThreads + tid;
+  if (col >= a.width) return;
+  const size_t pitch = static_cast<size_t>(2) * a.width;
+  const float* __restrict__ p = a.scratch + static_cast<size_t>(c_first) * pitch + col;
+  float acc = 0.f;
+#pragma unroll
+  for (int h = 0; h < kFixGroup; h += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = p[static_cast<size_t>(h + u) * pitch];
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      acc = (h + u == 0) ? v[u] : __fadd_rn(acc, v[u]);
+  }
+  a.group_part[static_cast<size_t>(g) * a.width + col] = acc;
+}
+
+// Fix-up, level 2: adds, in chunk order, the partials of every run that crosses
+// chunk edges: tail of the chunk where the run starts + heads of the following
+// chunks, whole "through" groups taken from level 1.  The chain length is found
+// first (all threads scan the head kinds), so the loads of the partial rows are
+// independent and issued sixteen at a time.  Every sum has a fixed association.
 template <typename T>
 __global__ void __launch_bounds__(kCtaThreads)
     BwdFixupKernel(const BwdArgs a) {
@@ -306,24 +346,34 @@ __global__ void __launch_bounds__(kCtaThreads)
     if (c < a.num_chunks && a.meta[c * 2 + 0] != kHeadThrough)
       atomicMin(&s_len, c - c0);
     __syncthreads();
-    if (s_len != 0x7fffffff) break;
+    const int found = s_len;
+    __syncthreads();  // everyone has read s_len before anyone updates it
+    if (found != 0x7fffffff) break;
   }
-  __syncthreads();
   int len = s_len;
-  if (len == 0x7fffffff) len = a.num_chunks - 1 - c0;  // malformed input guard
+  int last_through = c0 + len - 1;  // chunks c0+1 .. last_through are "through"
+  if (len == 0x7fffffff) {          // malformed input guard
+    len = a.num_chunks - 1 - c0;
+    last_through = c0 + len;
+  }
   // a "none" head at the end of the chain means the run ended exactly at the
   // chunk edge (cannot happen for a tail, kept as a guard): exclude it.
   if (c0 + len < a.num_chunks && a.meta[(c0 + len) * 2 + 0] == kHeadNone) --len;
 
   const int col = blockIdx.y * kCtaThreads + tid;
   if (col >= a.width) return;
-  const float* scratch = a.scratch;
+  const float* __restrict__ scratch = a.scratch;
   const size_t pitch = static_cast<size_t>(2) * a.width;
-  float acc = scratch[static_cast<size_t>(c0) * pitch + a.width + col];
-  int c = c0 + 1;
-  const int end = c0 + len;  // inclusive
   constexpr int kInFlight = 16;
-  for (; c + kInFlight - 1 <= end; c += kInFlight) {
+  float acc = scratch[static_cast<size_t>(c0) * pitch + a.width + col];
+  const int end = c0 + len;  // inclusive
+  // whole groups inside the "through" part of the chain: [g0, g1)
+  int g0 = (c0 + 1 + kFixGroup - 1) / kFixGroup;
+  int g1 = (last_through + 1) / kFixGroup;
+  if (g1 <= g0) g0 = g1 = 0x3fffffff / kFixGroup;  // none
+  const int lead_end = min(end, g0 * kFixGroup - 1);  // singles before the groups
+  int c = c0 + 1;
+  for (; c + kInFlight - 1 <= lead_end; c += kInFlight) {
     float v[kInFlight];
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u)
@@ -331,8 +381,32 @@ __global__ void __launch_bounds__(kCtaThreads)
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
   }
-  for (; c <= end; ++c)
+  for (; c <= lead_end; ++c)
     acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
+  if (c <= end && g1 > g0) {
+    const float* __restrict__ gp = a.group_part + col;
+    int g = g0;
+    for (; g + kInFlight <= g1; g += kInFlight) {
+      float v[kInFlight];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u)
+        v[u] = gp[static_cast<size_t>(g + u) * a.width];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
+    }
+    for (; g < g1; ++g) acc = __fadd_rn(acc, gp[static_cast<size_t>(g) * a.width]);
+    c = g1 * kFixGroup;
+    for (; c + kInFlight - 1 <= end; c += kInFlight) {
+      float v[kInFlight];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u)
+        v[u] = scratch[static_cast<size_t>(c + u) * pitch + col];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
+    }
+    for (; c <= end; ++c)
+      acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
+  }
   const long long row = a.meta_row[c0 * 2 + 1];
   StoreOneAs<T>(static_cast<T*>(a.grad) + row * a.width + col, acc);
 }
@@ -350,7 +424,7 @@ struct BwdLayout {
   int cta_nz;
   int num_ctas;
   int num_chunks;
-  size_t scratch_off, meta_off, row_off, total;
+  size_t scratch_off, group_off, meta_off, row_off, total;
 };
 
 BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
@@ -365,6 +439,9 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
     rounds = 1;
     while (rounds < 8 && static_cast<int64_t>(rounds) * 2 * kCtaThreads <= target)
       rounds *= 2;
+    // the same ~256 nonzeros per lane group whatever the row width (narrow
+    // rows use fewer lanes per group): keeps the chains of the fix-up short
+    if (rounds == 8) rounds = 8 * (32 / lanes);
   }
   L.rounds = rounds;
   L.cta_nz = rounds * kBwdThreads;
@@ -373,6 +450,9 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
   size_t off = 0;
   L.scratch_off = off;
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * embed_width * sizeof(float),
+                 256);
+  L.group_off = off;
+  off += AlignUp(static_cast<size_t>(L.num_chunks / kFixGroup + 1) * embed_width * sizeof(float),
                  256);
   L.meta_off = off;
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(int), 256);
@@ -392,9 +472,12 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   else
     BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8>
         <<<grid, kBwdThreads, 0, stream>>>(a);
-  dim3 fgrid(a.num_chunks, (a.width + kCtaThreads - 1) / kCtaThreads);
-  BwdFixupKernel<T><<<fgrid, kCtaThreads, 0, stream>>>(a);
-  CountLaunch(2);
+  const int wtiles = (a.width + kCtaThreads - 1) / kCtaThreads;
+  const int groups = a.num_chunks / kFixGroup;
+  if (groups > 0)
+    BwdGroupKernel<<<dim3(groups, wtiles), kCtaThreads, 0, stream>>>(a);
+  BwdFixupKernel<T><<<dim3(a.num_chunks, wtiles), kCtaThreads, 0, stream>>>(a);
+  CountLaunch(groups > 0 ? 3 : 2);
 }
 
 template <typename T, int V>
@@ -490,6 +573,7 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
   a.inverse_mapping =
       transpose_remapped_indices != nullptr ? inverse_mapping : nullptr;
   a.scratch = reinterpret_cast<float*>(work + L.scratch_off);
+  a.group_part = reinterpret_cast<float*>(work + L.group_off);
   a.meta = reinterpret_cast<int*>(work + L.meta_off);
   a.meta_row = reinterpret_cast<long long*>(work + L.row_off);
   a.row_bytes = row_bytes;
