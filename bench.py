@@ -413,6 +413,44 @@ def run_gpu(args):
         per_stage[k] /= args.steps
     ms_per_step = sum(per_stage.values())
 
+    # ---- extra (not part of `value`): the fused alternative to transpose +
+    # backward, SURVEY.md 8(f) f3: sort without the compressed-index pass, then
+    # backward fused with an SGD step on the table rows (lr = 0 keeps the table
+    # bits, every instruction still runs).
+    extras = {}
+    if not args.no_extras:
+        def transpose_nc():
+            ce.ExtractRowIdsFromFixed(batch, hot, row_ids)
+            ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+
+        def update():
+            ce.EmbeddingBackwardUpdate(grad_y, w, nnz, t_idx, t_sid, None, ce.OPT_SGD,
+                                       0.0, table, work=bwork)
+
+        ex_t = {"transpose_no_compress": 0.0, "backward_sgd_update": 0.0}
+        ex_ev = []
+        for it in range(3 + args.steps):
+            for name, fn in (("transpose_no_compress", transpose_nc),
+                             ("backward_sgd_update", update)):
+                flush.fill_(1)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                if it >= 3:
+                    ex_ev.append((name, e0, e1))
+        torch.cuda.synchronize()
+        for name, e0, e1 in ex_ev:
+            ex_t[name] += e0.elapsed_time(e1) / args.steps
+        extras["fused_sgd_step"] = {
+            "ms": {k: round(v, 4) for k, v in ex_t.items()},
+            "ms_total_with_forward": round(per_stage["forward"] + sum(ex_t.values()), 4),
+            "note": "forward + sort + backward fused with the SGD step on the table "
+                    "(no compressed indices, no gradient round trip); compare with "
+                    "ms_per_step, which leaves the gradient for a separate optimizer"}
+        transpose()  # restore remapped/t_idx for the e2e leg
+
     e2e_ms, h2d, d2h = float("nan"), 0, 0
     if not args.no_e2e:
         e2e_ms, h2d, d2h = run_e2e(args, ce, torch, dev, tdt, idt, cfg, idx_host, table,
@@ -501,6 +539,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "wall_s_timed_region": round(t_wall, 3),
+        "extras": extras,
     }
     print(json.dumps(line))
 
@@ -571,6 +610,8 @@ def main():
     ap.add_argument("--cpu-sample-bags", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra fused-optimizer measurement")
     ap.add_argument("--trace", default=None,
                     help="N > 1: write a CUPTI per-kernel time table of 5 extra steps here")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],

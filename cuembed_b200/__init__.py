@@ -7,15 +7,16 @@ operator interface plus the synthetic-workload generator used by the
 benchmark.  Importing the package does not touch the GPU; the first call
 loads (and if necessary builds) the library and fails loudly if it cannot.
 """
-from .api import (CombineMode, ComputeCompressedGradIndices, CuEmbedError,
-                  EmbeddingBackward, EmbeddingForward, ExtractRowIdsForConcat,
+from .api import (OPT_ADAGRAD, OPT_SGD, CombineMode, ComputeCompressedGradIndices, CuEmbedError,
+                  EmbeddingBackward, EmbeddingBackwardUpdate, EmbeddingForward,
+                  EmbeddingForwardMulti, ExtractRowIdsForConcat,
                   ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, ShardFinalize,
-                  ShardSelect, Transpose, backward_workspace_bytes,
-                  launch_count)
+                  ShardSelect, Transpose, backward_hot_units, set_backward_hot_path,
+                  backward_workspace_bytes, launch_count)
 
 __all__ = [
-    "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward",
+    "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward", "EmbeddingBackwardUpdate", "EmbeddingForwardMulti", "OPT_SGD", "OPT_ADAGRAD",
     "ExtractRowIdsFromFixed", "ExtractRowIdsFromCSR", "ExtractRowIdsForConcat",
     "Transpose", "ComputeCompressedGradIndices", "backward_workspace_bytes",
-    "launch_count", "ShardSelect", "ShardFinalize",
+    "backward_hot_units", "set_backward_hot_path", "launch_count", "ShardSelect", "ShardFinalize",
 ]

@@ -21,6 +21,11 @@ SIGNATURES = {
     "cuembed_error_string": (ctypes.c_char_p, [_ci]),
     "cuembed_forward": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci,
                               _ci, _ci, _vp, _ci, _vp]),
+    "cuembed_forward_multi": (_ci, [_ci, ctypes.POINTER(_vp), _ci, _ci,
+                                    ctypes.POINTER(_vp), _ci, ctypes.POINTER(_vp), _ci,
+                                    ctypes.POINTER(_vp), ctypes.POINTER(_ci),
+                                    ctypes.POINTER(_ci), ctypes.POINTER(_ci),
+                                    ctypes.POINTER(_vp), _ci, ctypes.c_longlong, _vp]),
     "cuembed_extract_row_ids_fixed": (_ci, [_ci, _ci, _vp, _ci, _vp]),
     "cuembed_extract_row_ids_csr": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp]),
     "cuembed_extract_row_ids_concat": (_ci, [_ci, _vp, _ci, _vp]),
@@ -31,6 +36,11 @@ SIGNATURES = {
                                _ci, _vp, _vp, _vp]),
     "cuembed_backward_ws": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp,
                                   _vp, _ci, _vp, _vp, _vp, _szp, _vp]),
+    "cuembed_backward_update": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _ci,
+                                      ctypes.c_float, ctypes.c_float, _vp, _vp, _vp,
+                                      _szp, _vp]),
+    "cuembed_set_backward_hot_path": (_ci, [_ci]),
+    "cuembed_backward_ws_hot_offset": (_ci, [_ci, _ci, _ci, _ci, _szp]),
     "cuembed_shard_select": (_ci, [_vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
                                    ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                    _vp, _vp, _szp, _vp]),

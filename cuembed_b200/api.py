@@ -215,6 +215,119 @@ def backward_workspace_bytes(dtype: torch.dtype, embed_width: int, nnz: int,
     return int(lwork.value)
 
 
+def EmbeddingForwardMulti(params, embed_width: int, indices, offsets, weights,
+                          batch_sizes, num_hots, modes, rets,
+                          out_row_stride: int = 0, stream=None) -> None:
+    """cuembed_forward_multi: pooled lookups into several tables of one row
+    shape in one launch (per 32 tables).  Lists of per-table tensors / ints;
+    `offsets` / `weights` may be None (all fixed-hotness / unweighted) or lists
+    whose entries may be None (offsets only).  `rets[t]` may be a strided view
+    into one [batch, num_tables * embed_width] matrix (pass its row stride in
+    elements as out_row_stride).  New functionality: the reference is
+    single-table (README.md:110)."""
+    lib = _lib.load()
+    n = len(params)
+    if n == 0:
+        return
+    vpa = ctypes.c_void_p * n
+    ia = ctypes.c_int * n
+
+    def ptrs(ts, name, need_contig=True):
+        out = []
+        for t in ts:
+            if t is None:
+                out.append(None)
+                continue
+            if not t.is_cuda:
+                raise CuEmbedError(
+                    f"{name} must be CUDA tensors: cuembed_b200 has no CPU fallback")
+            if need_contig and not t.is_contiguous():
+                raise CuEmbedError(f"{name} must be contiguous")
+            out.append(t.data_ptr())
+        return vpa(*out)
+
+    for t in rets:
+        if t.stride(-1) != 1 or (out_row_stride and t.dim() == 2 and t.shape[0] > 1
+                                 and t.stride(0) != out_row_stride):
+            raise CuEmbedError("rets must have unit column stride and the given row stride")
+    off_list = offsets if offsets is not None else [None] * n
+    first_off = next((o for o in off_list if o is not None), None)
+    w_arr = ptrs(weights, "weights") if weights is not None else None
+    modes_arr = ia(*[int(m) for m in modes]) if modes is not None else None
+    _check(lib.cuembed_forward_multi(
+        n, ptrs(params, "params"), _dt(params[0]), int(embed_width),
+        ptrs(indices, "indices"), _it(indices[0]),
+        ptrs(off_list, "offsets") if first_off is not None else None,
+        _it(first_off) if first_off is not None else 0, w_arr,
+        ia(*[int(b) for b in batch_sizes]), ia(*[int(h) for h in num_hots]),
+        modes_arr, ptrs(rets, "rets", need_contig=False), _dt(rets[0]),
+        int(out_row_stride), _stream(stream)))
+
+
+OPT_SGD = 1
+OPT_ADAGRAD = 2
+
+
+def EmbeddingBackwardUpdate(grad_y: torch.Tensor, embed_width: int, nnz: int,
+                            transpose_indices: torch.Tensor,
+                            transpose_sample_ids: torch.Tensor,
+                            transpose_weights: Optional[torch.Tensor],
+                            optimizer: int, lr: float, params: torch.Tensor,
+                            state: Optional[torch.Tensor] = None,
+                            eps: float = 1e-10,
+                            work: Optional[torch.Tensor] = None,
+                            stream=None) -> None:
+    """cuembed_backward_update: backward fused with a sparse optimizer step on
+    the touched rows of `params` (SGD, or Adagrad with an fp32 `state` of the
+    table's shape).  transpose_indices are table rows (no compressed indices).
+    The reference only lists this as a future kernel type (README.md:119)."""
+    lib = _lib.load()
+    if params.dtype != grad_y.dtype:
+        raise CuEmbedError("params must have the dtype of grad_y")
+    if transpose_weights is not None and transpose_weights.dtype != grad_y.dtype:
+        raise CuEmbedError("transpose_weights must have the dtype of grad_y")
+    if optimizer == OPT_ADAGRAD:
+        if state is None or state.dtype != torch.float32 or state.shape != params.shape:
+            raise CuEmbedError("Adagrad needs an fp32 state of the table's shape")
+    head = [_dev(grad_y, "grad_y"), _dt(grad_y), int(embed_width), int(nnz),
+            _it(transpose_indices)]
+    lwork = ctypes.c_size_t(0)
+    _check(lib.cuembed_backward_update(*head, None, None, None, int(optimizer),
+                                       float(lr), float(eps), None, None, None,
+                                       ctypes.byref(lwork), None))
+    if work is None:
+        work = torch.empty(lwork.value, dtype=torch.uint8, device=grad_y.device)
+    elif work.numel() < lwork.value:
+        raise CuEmbedError(f"workspace too small: {work.numel()} < {lwork.value}")
+    lwork = ctypes.c_size_t(work.numel())
+    _check(lib.cuembed_backward_update(
+        *head, _dev(transpose_indices, "transpose_indices"),
+        _dev(transpose_sample_ids, "transpose_sample_ids"),
+        _dev(transpose_weights, "transpose_weights"), int(optimizer), float(lr),
+        float(eps), _dev(params, "params"), _dev(state, "state"),
+        _dev(work, "work"), ctypes.byref(lwork), _stream(stream)))
+
+
+def set_backward_hot_path(enable: bool) -> bool:
+    """Process-wide switch of the experimental hot-row path of the backward
+    (include/cuembed_b200.h); returns the previous setting."""
+    return bool(_lib.load().cuembed_set_backward_hot_path(1 if enable else 0))
+
+
+def backward_hot_units(work: torch.Tensor, dtype: torch.dtype, embed_width: int,
+                       nnz: int, index_dtype: torch.dtype = torch.int32) -> int:
+    """Number of hot units the last EmbeddingBackward(..., work=work) found
+    (the hot-row path); -1 if that path is off for the shape.
+    Synchronises (reads 4 bytes of the workspace)."""
+    lib = _lib.load()
+    off = ctypes.c_size_t(0)
+    _check(lib.cuembed_backward_ws_hot_offset(_DT[dtype], int(embed_width), int(nnz),
+                                              _IT[index_dtype], ctypes.byref(off)))
+    if off.value == ctypes.c_size_t(-1).value:
+        return -1
+    return int(work[off.value:off.value + 4].view(torch.int32).item())
+
+
 # ---------------------------------------------------------------- sharded mode
 def ShardSelect(indices: torch.Tensor, offsets: Optional[torch.Tensor],
                 weights: Optional[torch.Tensor], batch_size: int, num_hots: int,

@@ -28,6 +28,8 @@
 //     embedding_lookup_ops.cuh:610-618, overflows at rows*width >= 2^31).
 //
 // L2/HBM-bound gather + stream-out: no tensor cores.
+#include <atomic>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -55,6 +57,21 @@ struct BwdArgs {
   int cta_nz;      // nonzeros per CTA = kBwdThreads * rounds
   int num_ctas;
   int num_chunks;  // = num_ctas * lane groups per CTA
+  // hot-row path (backward_hot.cuh); chunk_state == nullptr switches it off
+  int* hot_ctr;                // [0] hot units, [1] largest sample id
+  int2* hot_units;             // [hot_cap] {first chunk, number of chunks}
+  unsigned char* chunk_state;  // [num_chunks]
+  float* hot_partial;          // [hot_cap][kHotMaxRanges][width]
+  int hot_min_chunks;
+  int hot_cap;
+  int chunk_nz;  // nonzeros per chunk = lanes * rounds
+  int sm_slots;
+  // fused sparse optimizer step: opt_kind != 0 makes `grad`
+  // the TABLE and every finished row sum an in-place update of its table row
+  int opt_kind;      // CUEMBED_OPT_NONE / SGD / ADAGRAD
+  float opt_lr;
+  float opt_eps;
+  float* opt_state;  // Adagrad accumulator [rows][width] fp32
 };
 
 constexpr int kHeadNone = 0;
@@ -88,7 +105,7 @@ __device__ __forceinline__ void StoreOneAs<__nv_bfloat16>(__nv_bfloat16* p,
 
 constexpr int kBwdThreads = 128;
 #ifndef BWD_MINB
-#define BWD_MINB 7
+#define BWD_MINB 6
 #endif
 
 template <int NE>
@@ -108,7 +125,62 @@ __device__ __forceinline__ void StorePartial(float* dst, const float* acc) {
   }
 }
 
-template <typename T, int V, typename IdxT, bool WEIGHTED, int UNROLL>
+// One element of the fused optimizer step.  Every operation is rounded
+// separately (no FMA contraction) so a numpy float32 restatement reproduces it
+// bit for bit:  SGD      p <- p - lr * g
+//               Adagrad  s <- s + g * g;  p <- p - (lr * g) / (sqrt(s) + eps)
+__device__ __forceinline__ float OptStep(int kind, float lr, float eps, float p,
+                                         float g, float* state) {
+  if (kind == CUEMBED_OPT_ADAGRAD) {
+    const float s = __fadd_rn(*state, __fmul_rn(g, g));
+    *state = s;
+    return __fsub_rn(
+        p, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(__fsqrt_rn(s), eps)));
+  }
+  return __fsub_rn(p, __fmul_rn(lr, g));
+}
+
+// In-place update of NE consecutive elements of table row `row` with the
+// finished gradient sums g[NE] (one V-byte vector of the row per lane).
+template <typename T, int V, int NE>
+__device__ __forceinline__ void ApplyUpdateVec(
+    const BwdArgs& a, char* table_row, int64_t row, int64_t elem_off,
+    const float* g, typename VecBits<V>::type old_vec) {
+  using VecT = typename VecBits<V>::type;
+  constexpr int NW = V / 4;
+  VecT* pv = reinterpret_cast<VecT*>(table_row + elem_off * sizeof(T));
+  uint32_t w[NW];
+  Unpack32(old_vec, w);
+  float st[NE];
+  float* sp = nullptr;
+  if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
+    sp = a.opt_state + row * a.width + elem_off;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) st[e] = sp[e];
+  }
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    float f[Elem<T>::kPerWord];
+    Elem<T>::WordToFloat(w[i], f);
+#pragma unroll
+    for (int k = 0; k < Elem<T>::kPerWord; ++k) {
+      const int e = i * Elem<T>::kPerWord + k;
+      f[k] = OptStep(a.opt_kind, a.opt_lr, a.opt_eps, f[k], g[e], &st[e]);
+    }
+    w[i] = Elem<T>::FloatToWord(f);
+  }
+  VecT out;
+  Pack32(w, &out);
+  *pv = out;
+  if (sp != nullptr) StorePartial<NE>(sp, st);
+}
+
+}  // namespace cuembed_b200
+#include "backward_hot.cuh"
+namespace cuembed_b200 {
+
+template <typename T, int V, typename IdxT, bool WEIGHTED, int UNROLL,
+          bool FUSED_OPT>
 __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     BwdSegReduceKernel(const BwdArgs a) {
   using VecT = typename VecBits<V>::type;
@@ -144,6 +216,12 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
   int n_g = 0;
   if (c0 < a.nnz)
     n_g = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
+  // A chunk of a hot unit is summed by BwdHotKernel: nothing to walk here, it
+  // only reports itself as a "through" chunk (its head partial comes from
+  // BwdHotCombineKernel).  The lane group keeps running the warp-wide loops.
+  const bool hot_chunk =
+      a.chunk_state != nullptr && a.chunk_state[chunk] == kChunkHot;
+  if (hot_chunk) n_g = 0;
 
   const int v = blockIdx.y * G + lane_g;
   const bool active = v < a.nvec;
@@ -162,19 +240,39 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
 #pragma unroll
   for (int e = 0; e < NE; ++e) acc[e] = 0.f;
 
+  // The (key, sample, weight, next key, table row) of a round are requested one
+  // round ahead, so no index load sits in front of the row loads of a round
+  // (ncu: 8 % of the warp samples waited for keys[i + 1], another 8 % for the
+  // table row that inverse_mapping receives at every run end).
+  IdxT n_key = 0, n_sid = 0, n_knext = 0, n_tk = 0;
+  T n_w = T();
+  auto request = [&](int r) {
+    const int cnt = max(0, min(G, n_g - r * G));
+    const int64_t i = c0 + r * G + lane_g;
+    n_key = 0;
+    n_sid = 0;
+    n_knext = 0;
+    n_tk = 0;
+    n_w = T();
+    if (lane_g < cnt) {
+      n_key = __ldg(keys + i);
+      n_sid = __ldg(sids + i);
+      if constexpr (WEIGHTED) n_w = __ldg(weights + i);
+      if (i + 1 < a.nnz) n_knext = __ldg(keys + i + 1);
+      if (tidx != nullptr) n_tk = __ldg(tidx + i);
+    }
+  };
+  request(0);
+
 #pragma unroll 1
   for (int r = 0; r < a.rounds; ++r) {
     const int cnt = max(0, min(G, n_g - r * G));
     const int64_t i = c0 + r * G + lane_g;
-    IdxT key = 0, sid = 0;
-    T w = T();
-    bool end = false;
-    if (lane_g < cnt) {
-      key = __ldg(keys + i);
-      sid = __ldg(sids + i);
-      if constexpr (WEIGHTED) w = __ldg(weights + i);
-      end = (i == a.nnz - 1) || (__ldg(keys + i + 1) != key);
-    }
+    const IdxT key = n_key, sid = n_sid, tk = n_tk;
+    const T w = n_w;
+    const bool end =
+        lane_g < cnt && ((i == a.nnz - 1) || (n_knext != key));
+    if (r + 1 < a.rounds) request(r + 1);
     const unsigned endsw = __ballot_sync(kFull, end);
     const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(kFull, cnt);
 
@@ -182,6 +280,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     for (int jb = 0; jb < cnt_max; jb += UNROLL) {
       VecT vals[UNROLL];
       T wv[UNROLL];
+      VecT pold[FUSED_OPT ? UNROLL : 1];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int src = (jb + u) & (G - 1);
@@ -195,7 +294,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
           if constexpr (sizeof(T) == 4) {
             wv[u] = __shfl_sync(kFull, w, src, G);
           } else {
-            unsigned short b = *reinterpret_cast<unsigned short*>(&w);
+            const unsigned short b = *reinterpret_cast<const unsigned short*>(&w);
             unsigned rb = __shfl_sync(kFull, static_cast<unsigned>(b), src, G);
             unsigned short rs = static_cast<unsigned short>(rb);
             wv[u] = *reinterpret_cast<T*>(&rs);
@@ -204,6 +303,17 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
         // Positions past the end of the chunk carry sample id 0: a valid,
         // harmless load that is never accumulated.
         vals[u] = LdgVec<V>(gy + GradRowOffset<IdxT>(s, row_bytes));
+        // Fused optimizer: the table row that a run ending at this position
+        // will update is requested together with the gradient rows, so the
+        // read-modify-write does not wait for DRAM at every run end.
+        if constexpr (FUSED_OPT) {
+          const IdxT kr = ShflIdx<IdxT>(key, src, G);
+          pold[u] = VecT();
+          if (active && jb + u < G && ((endsw >> (gl0 + jb + u)) & 1u) != 0u)
+            pold[u] = *reinterpret_cast<const VecT*>(
+                static_cast<const char*>(a.grad) +
+                GradRowOffset<IdxT>(kr, row_bytes) + static_cast<int64_t>(v) * V);
+        }
       }
       // Fast path: a full batch in which no lane group of the warp ends a run
       // (the interior of long runs, ~half of all nonzeros under a power law).
@@ -234,12 +344,8 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
         }
         // Warp-uniform test: does any lane group of this warp end a run at j?
         if (j < G && (endsw & (patt << j)) != 0u) {
-          IdxT krow;
-          if constexpr (sizeof(IdxT) == 8)
-            krow = static_cast<IdxT>(
-                __shfl_sync(kFull, static_cast<long long>(key), j, G));
-          else
-            krow = __shfl_sync(kFull, key, j, G);
+          const IdxT krow = ShflIdx<IdxT>(key, j, G);
+          const IdxT trow = ShflIdx<IdxT>(tk, j, G);
           if (((endsw >> (gl0 + j)) & 1u) != 0u) {
             if (in_first && cont) {
               // Run began in an earlier chunk: partial, added by the fix-up.
@@ -247,15 +353,19 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
               head_kind = kHeadEnds;
               head_row = krow;
             } else if (active) {
-              StoreFloatsAs<NE>(static_cast<char*>(a.grad) +
-                                    GradRowOffset<IdxT>(krow, row_bytes),
-                                static_cast<int64_t>(v) * NE, Elem<T>::kCode,
-                                acc);
+              char* out_row = static_cast<char*>(a.grad) +
+                              GradRowOffset<IdxT>(krow, row_bytes);
+              if constexpr (!FUSED_OPT)
+                StoreFloatsAs<NE>(out_row, static_cast<int64_t>(v) * NE,
+                                  Elem<T>::kCode, acc);
+              else
+                ApplyUpdateVec<T, V, NE>(a, out_row, static_cast<int64_t>(krow),
+                                         static_cast<int64_t>(v) * NE, acc,
+                                         pold[FUSED_OPT ? u : 0]);
             }
             if (a.inverse_mapping != nullptr && lane_g == 0 &&
                 blockIdx.y == 0) {
-              static_cast<IdxT*>(a.inverse_mapping)[krow] =
-                  __ldg(tidx + c0 + r * G + j);
+              static_cast<IdxT*>(a.inverse_mapping)[krow] = trow;
             }
 #pragma unroll
             for (int e = 0; e < NE; ++e) acc[e] = 0.f;
@@ -280,6 +390,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
       if (active) StorePartial<NE>(my_tail + v * NE, acc);
     }
   }
+  if (hot_chunk) head_kind = kHeadThrough;
   if (lane_g == 0 && blockIdx.y == 0) {
     a.meta[chunk * 2 + 0] = head_kind;
     a.meta[chunk * 2 + 1] = has_tail;
@@ -331,6 +442,8 @@ __global__ void __launch_bounds__(kCtaThreads)
 // chunks, whole "through" groups taken from level 1.  The chain length is found
 // first (all threads scan the head kinds), so the loads of the partial rows are
 // independent and issued sixteen at a time.  Every sum has a fixed association.
+// (A warp-per-chunk variant with 8 x 8 loads in flight per lane was measured
+// slower, 38 vs 30 us at C2: fewer resident warps per dependent round trip.)
 template <typename T>
 __global__ void __launch_bounds__(kCtaThreads)
     BwdFixupKernel(const BwdArgs a) {
@@ -408,7 +521,20 @@ __global__ void __launch_bounds__(kCtaThreads)
       acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
   }
   const long long row = a.meta_row[c0 * 2 + 1];
-  StoreOneAs<T>(static_cast<T*>(a.grad) + row * a.width + col, acc);
+  T* dst = static_cast<T*>(a.grad) + row * a.width + col;
+  if (a.opt_kind != CUEMBED_OPT_NONE) {
+    // fused optimizer step: the finished sum updates the table element
+    float st = 0.f;
+    float* sp = nullptr;
+    if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
+      sp = a.opt_state + row * a.width + col;
+      st = *sp;
+    }
+    acc = OptStep(a.opt_kind, a.opt_lr, a.opt_eps, Elem<T>::ToFloat(*dst), acc,
+                  &st);
+    if (sp != nullptr) *sp = st;
+  }
+  StoreOneAs<T>(dst, acc);
 }
 
 namespace {
@@ -425,9 +551,34 @@ struct BwdLayout {
   int num_ctas;
   int num_chunks;
   size_t scratch_off, group_off, meta_off, row_off, total;
+  // hot-row path
+  bool hot;
+  int hot_min_chunks, hot_cap;
+  size_t hot_ctr_off, hot_units_off, state_off, hot_partial_off;
 };
 
-BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
+// Hot-row path (experimental, OFF by default: measured slower on B200, see
+// DESIGN.md 3.3): rows of 16-byte vectors up to 2 KB, and enough nonzeros for a
+// hot unit to exist at all.  cuembed_set_backward_hot_path(1) or
+// CUEMBED_BWD_HOT=1 switch it on, CUEMBED_BWD_HOT_NNZ sets the smallest hot
+// unit (nonzeros).
+std::atomic<int> g_hot_path{-1};  // -1: not decided yet (environment)
+
+int BackwardHotPathEnabled() {
+  int v = g_hot_path.load();
+  if (v < 0) {
+    v = EnvInt("CUEMBED_BWD_HOT", 0) != 0 ? 1 : 0;
+    g_hot_path.store(v);
+  }
+  return v;
+}
+
+bool HotPathShape(int embed_width, int dtype) {
+  const int64_t row_bytes = static_cast<int64_t>(embed_width) * ElemSize(dtype);
+  return row_bytes % 16 == 0 && row_bytes >= 64 && row_bytes <= 2048;
+}
+
+BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
   BwdLayout L;
   static const int rounds_env = EnvInt("CUEMBED_BWD_ROUNDS", 0);
   int rounds = rounds_env;
@@ -458,19 +609,74 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes) {
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(int), 256);
   L.row_off = off;
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(long long), 256);
+  const int hot_env = BackwardHotPathEnabled();
+  static const int hot_nnz = EnvInt("CUEMBED_BWD_HOT_NNZ", 2048);
+  const int chunk_nz = lanes * rounds;
+  L.hot_min_chunks = (hot_nnz + chunk_nz - 1) / chunk_nz;
+  if (L.hot_min_chunks < 4) L.hot_min_chunks = 4;
+  L.hot = hot_env != 0 && HotPathShape(embed_width, dtype) &&
+          L.num_chunks >= 2 * L.hot_min_chunks;
+  L.hot_cap = 0;
+  L.hot_ctr_off = L.hot_units_off = L.state_off = L.hot_partial_off = off;
+  if (L.hot) {
+    L.hot_cap = L.num_chunks / L.hot_min_chunks + 1;
+    L.hot_ctr_off = off;
+    off += 256;
+    L.hot_units_off = off;
+    off += AlignUp(static_cast<size_t>(L.hot_cap) * sizeof(int2), 256);
+    L.state_off = off;
+    off += AlignUp(static_cast<size_t>(L.num_chunks), 256);
+    L.hot_partial_off = off;
+    off += AlignUp(static_cast<size_t>(L.hot_cap) * kHotMaxRanges * embed_width *
+                       sizeof(float),
+                   256);
+  }
   L.total = off > 0 ? off : 256;
   return L;
 }
 
+template <typename T, typename IdxT, bool WEIGHTED, int NV>
+void LaunchHot(const BwdArgs& a, cudaStream_t stream) {
+  constexpr int NE = 4 * Elem<T>::kPerWord;
+  constexpr int RPW = (NV * NE >= 32) ? 2 : 4;
+  constexpr int kRpc = kHotWarps * RPW;
+  auto kernel = BwdHotKernel<T, IdxT, WEIGHTED, NV, RPW>;
+  static bool configured = false;  // benign race: same value from every thread
+  if (!configured) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kHotSmemBytes);
+    configured = true;
+  }
+  const int warp_ctas = (a.num_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
+  BwdHotScanAKernel<IdxT><<<warp_ctas, kCtaThreads, 0, stream>>>(a);
+  BwdHotScanBKernel<IdxT><<<warp_ctas, kCtaThreads, 0, stream>>>(a);
+  const int max_groups = (a.hot_cap + kRpc - 1) / kRpc;
+  kernel<<<dim3(kHotMaxRanges, max_groups), kHotThreads, kHotSmemBytes,
+           stream>>>(a);
+  const int wtiles = (a.width + kCtaThreads - 1) / kCtaThreads;
+  BwdHotCombineKernel<<<dim3(a.hot_cap, wtiles), kCtaThreads, 0, stream>>>(
+      a, kRpc);
+  CountLaunch(4);
+}
+
 template <typename T, int V, typename IdxT, bool WEIGHTED>
 void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
-  static const int unroll = EnvInt("CUEMBED_BWD_UNROLL", 8);
+  if constexpr (V == 16) {
+    if (a.chunk_state != nullptr) {
+      if (a.nvec <= 32)
+        LaunchHot<T, IdxT, WEIGHTED, 1>(a, stream);
+      else if (a.nvec <= 64)
+        LaunchHot<T, IdxT, WEIGHTED, 2>(a, stream);
+      else
+        LaunchHot<T, IdxT, WEIGHTED, 4>(a, stream);
+    }
+  }
   dim3 grid(a.num_ctas, col_tiles);
-  if (unroll == 4)
-    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4>
+  if (a.opt_kind != CUEMBED_OPT_NONE)
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4, true>
         <<<grid, kBwdThreads, 0, stream>>>(a);
   else
-    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8>
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8, false>
         <<<grid, kBwdThreads, 0, stream>>>(a);
   const int wtiles = (a.width + kCtaThreads - 1) / kCtaThreads;
   const int groups = a.num_chunks / kFixGroup;
@@ -509,6 +715,42 @@ void LaunchSegReduceVec(const BwdArgs& a, int vec_bytes, int idx_type,
 
 }  // namespace
 
+int SetBackwardHotPath(int enable) {
+  const int before = BackwardHotPathEnabled();
+  g_hot_path.store(enable != 0 ? 1 : 0);
+  return before;
+}
+
+int BackwardHotCounterOffset(int dtype, int embed_width, int nnz, int idx_type,
+                             size_t* offset) {
+  if (offset == nullptr || nnz < 0 || embed_width <= 0)
+    return CUEMBED_ERR_ARGUMENT;
+  if (dtype < 0 || dtype > 2 || idx_type < 0 || idx_type > 1)
+    return CUEMBED_ERR_DTYPE;
+  RowShape shape;
+  if (!MakeRowShape(embed_width, dtype, &shape)) return CUEMBED_ERR_ROW_BYTES;
+  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes, dtype);
+  *offset = L.hot ? L.hot_ctr_off : static_cast<size_t>(-1);
+  return CUEMBED_OK;
+}
+
+namespace {
+struct OptParams {
+  int kind;
+  float lr, eps;
+  float* state;
+};
+
+int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
+                       int num_grad_embedding_rows, int nnz, int idx_type,
+                       const void* transpose_indices,
+                       const void* transpose_sample_ids,
+                       const void* transpose_remapped_indices,
+                       const void* transpose_weights, int skip_grad_init,
+                       void* grad_embedding, void* inverse_mapping, char* work,
+                       size_t* lwork, const OptParams& opt, cudaStream_t stream);
+}  // namespace
+
 int LaunchBackward(const void* grad_y, int dtype, int embed_width,
                    int num_grad_embedding_rows, int nnz, int idx_type,
                    const void* transpose_indices,
@@ -517,6 +759,48 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
                    const void* transpose_weights, int skip_grad_init,
                    void* grad_embedding, void* inverse_mapping, char* work,
                    size_t* lwork, cudaStream_t stream) {
+  const OptParams none = {CUEMBED_OPT_NONE, 0.f, 0.f, nullptr};
+  return LaunchBackwardImpl(grad_y, dtype, embed_width, num_grad_embedding_rows,
+                            nnz, idx_type, transpose_indices,
+                            transpose_sample_ids, transpose_remapped_indices,
+                            transpose_weights, skip_grad_init, grad_embedding,
+                            inverse_mapping, work, lwork, none, stream);
+}
+
+// Fused backward + sparse optimizer step (the reference
+// lists "optimizer" as a future kernel type, README.md:119): the row sums of
+// the backward are applied to the table in place instead of being written out
+// as a gradient, so neither the compressed-index pass nor the gradient round
+// trip (293 MB at C2) exists.
+int LaunchBackwardUpdate(const void* grad_y, int dtype, int embed_width, int nnz,
+                         int idx_type, const void* transpose_indices,
+                         const void* transpose_sample_ids,
+                         const void* transpose_weights, int optimizer, float lr,
+                         float eps, void* params, float* state, char* work,
+                         size_t* lwork, cudaStream_t stream) {
+  if (optimizer != CUEMBED_OPT_SGD && optimizer != CUEMBED_OPT_ADAGRAD)
+    return CUEMBED_ERR_ARGUMENT;
+  if (work != nullptr && nnz > 0 &&
+      (params == nullptr ||
+       (optimizer == CUEMBED_OPT_ADAGRAD && state == nullptr)))
+    return CUEMBED_ERR_ARGUMENT;
+  const OptParams opt = {optimizer, lr, eps, state};
+  return LaunchBackwardImpl(grad_y, dtype, embed_width, 0, nnz, idx_type,
+                            transpose_indices, transpose_sample_ids, nullptr,
+                            transpose_weights, /*skip_grad_init=*/1, params,
+                            nullptr, work, lwork, opt, stream);
+}
+
+namespace {
+int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
+                       int num_grad_embedding_rows, int nnz, int idx_type,
+                       const void* transpose_indices,
+                       const void* transpose_sample_ids,
+                       const void* transpose_remapped_indices,
+                       const void* transpose_weights, int skip_grad_init,
+                       void* grad_embedding, void* inverse_mapping, char* work,
+                       size_t* lwork, const OptParams& opt,
+                       cudaStream_t stream) {
   if (lwork == nullptr || nnz < 0 || embed_width <= 0 ||
       num_grad_embedding_rows < 0)
     return CUEMBED_ERR_ARGUMENT;
@@ -528,7 +812,7 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
   // a misaligned call uses narrower vectors, i.e. fewer, wider lane groups.
   RowShape shape;
   MakeRowShape(embed_width, dtype, &shape);
-  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes);
+  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes, dtype);
   if (work == nullptr) {
     *lwork = L.total;
     return CUEMBED_OK;
@@ -586,6 +870,22 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
   a.cta_nz = L.cta_nz;
   a.num_ctas = L.num_ctas;
   a.num_chunks = L.num_ctas * (kBwdThreads / a.lanes);
+  a.opt_kind = opt.kind;
+  a.opt_lr = opt.lr;
+  a.opt_eps = opt.eps;
+  a.opt_state = opt.state;
+  a.chunk_nz = a.lanes * a.rounds;
+  a.sm_slots = GetDeviceInfo().sm_count;
+  a.hot_min_chunks = L.hot_min_chunks;
+  a.hot_cap = L.hot_cap;
+  a.hot_ctr = reinterpret_cast<int*>(work + L.hot_ctr_off);
+  a.hot_units = reinterpret_cast<int2*>(work + L.hot_units_off);
+  a.hot_partial = reinterpret_cast<float*>(work + L.hot_partial_off);
+  // the layout was sized for the aligned row shape: a call whose pointers only
+  // allow narrower vectors (different chunking) takes the plain path
+  a.chunk_state = (L.hot && v == 16 && a.lanes == shape.lanes)
+                      ? reinterpret_cast<unsigned char*>(work + L.state_off)
+                      : nullptr;
   const int col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
   const bool weighted = transpose_weights != nullptr;
 
@@ -598,5 +898,6 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
                                       stream);
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
+}  // namespace
 
 }  // namespace cuembed_b200

@@ -67,6 +67,20 @@ int cuembed_forward(const void* params, int in_dtype, int embed_width,
                        reinterpret_cast<cudaStream_t>(stream));
 }
 
+int cuembed_forward_multi(int num_tables, const void* const* params,
+                          int in_dtype, int embed_width,
+                          const void* const* indices, int idx_type,
+                          const void* const* offsets, int off_type,
+                          const void* const* weights, const int* batch_sizes,
+                          const int* num_hots, const int* modes,
+                          void* const* rets, int out_dtype,
+                          long long out_row_stride, cuembed_stream_t stream) {
+  return LaunchForwardMulti(num_tables, params, in_dtype, embed_width, indices,
+                            idx_type, offsets, off_type, weights, batch_sizes,
+                            num_hots, modes, rets, out_dtype, out_row_stride,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
 int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
                                   int idx_type, cuembed_stream_t stream) {
   return LaunchExtractRowIdsFixed(batch_size, num_hots, row_ids, idx_type,
@@ -118,6 +132,29 @@ int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
                         transpose_remapped_indices, transpose_weights,
                         skip_grad_init, grad_embedding, inverse_mapping, work,
                         lwork, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_backward_update(const void* grad_y, int dtype, int embed_width,
+                            int nnz, int idx_type,
+                            const void* transpose_indices,
+                            const void* transpose_sample_ids,
+                            const void* transpose_weights, int optimizer,
+                            float lr, float eps, void* params, float* state,
+                            char* work, size_t* lwork, cuembed_stream_t stream) {
+  return LaunchBackwardUpdate(grad_y, dtype, embed_width, nnz, idx_type,
+                              transpose_indices, transpose_sample_ids,
+                              transpose_weights, optimizer, lr, eps, params,
+                              state, work, lwork,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_set_backward_hot_path(int enable) {
+  return SetBackwardHotPath(enable);
+}
+
+int cuembed_backward_ws_hot_offset(int dtype, int embed_width, int nnz,
+                                   int idx_type, size_t* offset) {
+  return BackwardHotCounterOffset(dtype, embed_width, nnz, idx_type, offset);
 }
 
 // Scratch for the drop-in signature (no workspace argument): a library-owned

@@ -19,6 +19,8 @@
 // HBM/L2-bound byte work: no tensor cores (nothing here is a contraction).
 #include "common.cuh"
 #include "forward_kernels.cuh"
+#include <algorithm>
+
 #include "launch.h"
 
 namespace cuembed_b200 {
@@ -134,7 +136,154 @@ int CommonAlign(uint64_t bits) {
   return v;
 }
 
+template <typename T, int V, typename IdxT>
+void LaunchPoolMulti(const FwdMultiArgs& m, int num_tables, int col_tiles,
+                     int lanes, int max_batch, bool weighted,
+                     cudaStream_t stream) {
+  const int groups_per_cta = kCtaThreads / lanes;
+  const int64_t work_ctas = (max_batch + groups_per_cta - 1) / groups_per_cta;
+  static int occ_w = 0, occ_u = 0;
+  int grid;
+  if (weighted) {
+    auto k = FwdPoolMultiKernel<T, V, IdxT, true>;
+    grid = PersistentGrid(reinterpret_cast<const void*>(k), &occ_w, work_ctas);
+    grid = std::max(1, std::min<int>(grid, (grid + num_tables - 1) / num_tables * 2));
+    k<<<dim3(grid, col_tiles, num_tables), kCtaThreads, 0, stream>>>(m);
+  } else {
+    auto k = FwdPoolMultiKernel<T, V, IdxT, false>;
+    grid = PersistentGrid(reinterpret_cast<const void*>(k), &occ_u, work_ctas);
+    grid = std::max(1, std::min<int>(grid, (grid + num_tables - 1) / num_tables * 2));
+    k<<<dim3(grid, col_tiles, num_tables), kCtaThreads, 0, stream>>>(m);
+  }
+  CountLaunch();
+}
+
+template <typename T, typename IdxT>
+void LaunchPoolMultiVec(const FwdMultiArgs& m, int num_tables, int vec_bytes,
+                        int col_tiles, int lanes, int max_batch, bool weighted,
+                        cudaStream_t stream) {
+  if (vec_bytes == 16)
+    LaunchPoolMulti<T, 16, IdxT>(m, num_tables, col_tiles, lanes, max_batch,
+                                 weighted, stream);
+  else if (vec_bytes == 8)
+    LaunchPoolMulti<T, 8, IdxT>(m, num_tables, col_tiles, lanes, max_batch,
+                                weighted, stream);
+  else
+    LaunchPoolMulti<T, 4, IdxT>(m, num_tables, col_tiles, lanes, max_batch,
+                                weighted, stream);
+}
+
 }  // namespace
+
+// Multi-table batched forward: tables of one dtype, width, index type and
+// weighted-ness; batch size, hotness / CSR and sum / mean may differ per table.
+// HOST arrays of num_tables entries.  out_row_stride (elements of out_dtype,
+// 0 = embed_width) lets the pooled rows of all tables land in one
+// [batch, num_tables * embed_width] activation matrix.
+int LaunchForwardMulti(int num_tables, const void* const* params, int in_dtype,
+                       int embed_width, const void* const* indices,
+                       int idx_type, const void* const* offsets, int off_type,
+                       const void* const* weights, const int* batch_sizes,
+                       const int* num_hots, const int* modes, void* const* rets,
+                       int out_dtype, long long out_row_stride,
+                       cudaStream_t stream) {
+  if (num_tables < 0 || embed_width <= 0) return CUEMBED_ERR_ARGUMENT;
+  if (num_tables == 0) return CUEMBED_OK;
+  if (params == nullptr || indices == nullptr || batch_sizes == nullptr ||
+      num_hots == nullptr || rets == nullptr)
+    return CUEMBED_ERR_ARGUMENT;
+  if (in_dtype < 0 || in_dtype > 2 || out_dtype < 0 || out_dtype > 2 ||
+      idx_type < 0 || idx_type > 1)
+    return CUEMBED_ERR_DTYPE;
+  const int64_t row_bytes =
+      static_cast<int64_t>(embed_width) * ElemSize(in_dtype);
+  if (row_bytes % 4 != 0) return CUEMBED_ERR_ROW_BYTES;
+  if (out_row_stride == 0) out_row_stride = embed_width;
+  if (out_row_stride < embed_width) return CUEMBED_ERR_ARGUMENT;
+  const int64_t out_row_bytes = out_row_stride * ElemSize(out_dtype);
+  RowShape shape;
+  MakeRowShape(embed_width, in_dtype, &shape);
+
+  // One vector width for the launch: limited by every pointer and pitch.
+  bool weighted = false, any = false;
+  uint64_t in_bits = static_cast<uint64_t>(row_bytes);
+  uint64_t out_bits = static_cast<uint64_t>(out_row_bytes);
+  for (int t = 0; t < num_tables; ++t) {
+    const int mode = modes != nullptr ? modes[t] : CUEMBED_SUM;
+    const void* off = offsets != nullptr ? offsets[t] : nullptr;
+    const void* w = weights != nullptr ? weights[t] : nullptr;
+    if (mode != CUEMBED_SUM && mode != CUEMBED_MEAN) return CUEMBED_ERR_DTYPE;
+    if (!((off != nullptr && num_hots[t] == 0) ||
+          (off == nullptr && num_hots[t] > 0)))
+      return CUEMBED_ERR_CSR_XOR_FIXED;
+    if (batch_sizes[t] < 0) return CUEMBED_ERR_ARGUMENT;
+    if (batch_sizes[t] == 0) continue;
+    if (params[t] == nullptr || indices[t] == nullptr || rets[t] == nullptr)
+      return CUEMBED_ERR_ARGUMENT;
+    if (any && (w != nullptr) != weighted) return CUEMBED_ERR_ARGUMENT;
+    weighted = w != nullptr;
+    any = true;
+    in_bits |= reinterpret_cast<uint64_t>(params[t]);
+    out_bits |= reinterpret_cast<uint64_t>(rets[t]);
+  }
+  if (!any) return CUEMBED_OK;
+  int v = shape.vec_bytes;
+  for (;;) {
+    const int64_t out_vec =
+        static_cast<int64_t>(v) * ElemSize(out_dtype) / ElemSize(in_dtype);
+    const bool ok = (in_bits % v == 0) &&
+                    (out_bits % (out_vec > 16 ? 16 : out_vec) == 0);
+    if (ok || v == 4) break;
+    v /= 2;
+  }
+  if (v < 4 || in_bits % v != 0) return CUEMBED_ERR_ARGUMENT;
+
+  const int nvec = static_cast<int>(row_bytes / v);
+  const int lanes = Pow2Ceil(nvec) < 32 ? Pow2Ceil(nvec) : 32;
+  const int col_tiles = (nvec + lanes - 1) / lanes;
+  for (int t0 = 0; t0 < num_tables; t0 += kMaxTablesPerLaunch) {
+    FwdMultiArgs m;
+    int n = 0, max_batch = 0;
+    for (int t = t0; t < num_tables && t < t0 + kMaxTablesPerLaunch; ++t) {
+      if (batch_sizes[t] == 0) continue;
+      FwdArgs& a = m.t[n++];
+      a.params = params[t];
+      a.indices = indices[t];
+      a.offsets = offsets != nullptr ? offsets[t] : nullptr;
+      a.weights = weights != nullptr ? weights[t] : nullptr;
+      a.out = rets[t];
+      a.row_bytes = row_bytes;
+      a.out_row_bytes = out_row_bytes;
+      a.batch = batch_sizes[t];
+      a.num_hots = num_hots[t];
+      a.off64 = (off_type == CUEMBED_I64);
+      a.mean = (modes != nullptr && modes[t] == CUEMBED_MEAN);
+      a.out_dt = out_dtype;
+      a.nvec = nvec;
+      a.lanes = lanes;
+      a.log2_lanes = Log2(lanes);
+      a.col_tiles = col_tiles;
+      if (a.batch > max_batch) max_batch = a.batch;
+    }
+    if (n == 0) continue;
+#define MULTI_CASE(TT)                                                        \
+  if (idx_type == CUEMBED_I64)                                                \
+    LaunchPoolMultiVec<TT, int64_t>(m, n, v, col_tiles, lanes, max_batch,     \
+                                    weighted, stream);                        \
+  else                                                                        \
+    LaunchPoolMultiVec<TT, int32_t>(m, n, v, col_tiles, lanes, max_batch,     \
+                                    weighted, stream)
+    if (in_dtype == CUEMBED_F32) {
+      MULTI_CASE(float);
+    } else if (in_dtype == CUEMBED_F16) {
+      MULTI_CASE(__half);
+    } else {
+      MULTI_CASE(__nv_bfloat16);
+    }
+#undef MULTI_CASE
+  }
+  return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+}
 
 int LaunchForward(const void* params, int in_dtype, int embed_width,
                   const void* indices, int idx_type, const void* offsets,

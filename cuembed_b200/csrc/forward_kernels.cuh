@@ -167,8 +167,7 @@ __device__ __forceinline__ uint64_t RowOffset(IdxT row, uint32_t row_bytes) {
 
 template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP,
           int UNROLL>
-__global__ void __launch_bounds__(kCtaThreads, FWD_MINB(UNROLL))
-    FwdPoolKernel(const FwdArgs a) {
+__device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
   using VecT = typename VecBits<V>::type;
   using AccT = Accum<T, V, LOWP>;
   constexpr unsigned kFull = 0xffffffffu;
@@ -290,6 +289,30 @@ __global__ void __launch_bounds__(kCtaThreads, FWD_MINB(UNROLL))
       acc.Store(static_cast<char*>(a.out) + bag * a.out_row_bytes,
                 static_cast<int64_t>(v) * AccT::NE, a.out_dt);
   }
+}
+
+template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP,
+          int UNROLL>
+__global__ void __launch_bounds__(kCtaThreads, FWD_MINB(UNROLL))
+    FwdPoolKernel(const FwdArgs a) {
+  FwdPoolBody<T, V, IdxT, WEIGHTED, LOWP, UNROLL>(a);
+}
+
+// Multi-table batched lookup (the reference is "single
+// table", README.md:110): up to kMaxTablesPerLaunch pooled lookups of the same
+// row shape in ONE launch, grid.z = table.  The descriptors travel as a
+// __grid_constant__ kernel parameter (constant bank, no device-side descriptor
+// buffer, CUDA-graph capturable); each table gets an equal share of a
+// persistent grid, so many small tables cost one launch instead of one each.
+constexpr int kMaxTablesPerLaunch = 32;
+struct FwdMultiArgs {
+  FwdArgs t[kMaxTablesPerLaunch];
+};
+
+template <typename T, int V, typename IdxT, bool WEIGHTED>
+__global__ void __launch_bounds__(kCtaThreads, FWD_MINB(8))
+    FwdPoolMultiKernel(const __grid_constant__ FwdMultiArgs m) {
+  FwdPoolBody<T, V, IdxT, WEIGHTED, false, 8>(m.t[blockIdx.z]);
 }
 
 // Concat: out[nz, :] = params[indices[nz], :], a pure row gather

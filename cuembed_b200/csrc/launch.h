@@ -19,6 +19,14 @@ int LaunchForward(const void* params, int in_dtype, int embed_width,
                   int num_hots, int mode, int fp16_math, void* ret,
                   int out_dtype, cudaStream_t stream);
 
+int LaunchForwardMulti(int num_tables, const void* const* params, int in_dtype,
+                       int embed_width, const void* const* indices,
+                       int idx_type, const void* const* offsets, int off_type,
+                       const void* const* weights, const int* batch_sizes,
+                       const int* num_hots, const int* modes, void* const* rets,
+                       int out_dtype, long long out_row_stride,
+                       cudaStream_t stream);
+
 int LaunchExtractRowIdsFixed(int batch_size, int num_hots, void* row_ids,
                              int idx_type, cudaStream_t stream);
 int LaunchExtractRowIdsCsr(const void* offsets, int off_type, int batch_size,
@@ -44,6 +52,17 @@ int LaunchBackward(const void* grad_y, int dtype, int embed_width,
                    const void* transpose_weights, int skip_grad_init,
                    void* grad_embedding, void* inverse_mapping, char* work,
                    size_t* lwork, cudaStream_t stream);
+
+int LaunchBackwardUpdate(const void* grad_y, int dtype, int embed_width, int nnz,
+                         int idx_type, const void* transpose_indices,
+                         const void* transpose_sample_ids,
+                         const void* transpose_weights, int optimizer, float lr,
+                         float eps, void* params, float* state, char* work,
+                         size_t* lwork, cudaStream_t stream);
+
+int SetBackwardHotPath(int enable);
+int BackwardHotCounterOffset(int dtype, int embed_width, int nnz, int idx_type,
+                             size_t* offset);
 
 int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
                       int off_type, const void* weights, int weight_dtype,

@@ -91,6 +91,28 @@ int cuembed_forward(const void* params, int in_dtype, int embed_width,
                     int num_hots, int mode, int fp16_math, void* ret,
                     int out_dtype, cuembed_stream_t stream);
 
+/*
+ * Multi-table batched lookup (new; the reference is "single table",
+ * README.md:110): num_tables pooled lookups in one launch per 32 tables.  All
+ * tables share in_dtype, embed_width, idx_type, off_type, out_dtype and
+ * weighted-ness (weights == NULL, or one non-NULL pointer per table); batch
+ * size, fixed hotness / CSR offsets and the mode (CUEMBED_SUM / CUEMBED_MEAN;
+ * modes == NULL means sum) are per table.  params / indices / offsets /
+ * weights / rets / batch_sizes / num_hots / modes are HOST arrays of num_tables
+ * entries (device pointers inside).  out_row_stride is the pitch of every
+ * output in elements of out_dtype (0 = embed_width), so all tables can write
+ * their slice of one [batch, num_tables * embed_width] matrix.  Every table's
+ * result is bit-identical to its own cuembed_forward call.
+ */
+int cuembed_forward_multi(int num_tables, const void* const* params,
+                          int in_dtype, int embed_width,
+                          const void* const* indices, int idx_type,
+                          const void* const* offsets, int off_type,
+                          const void* const* weights, const int* batch_sizes,
+                          const int* num_hots, const int* modes,
+                          void* const* rets, int out_dtype,
+                          long long out_row_stride, cuembed_stream_t stream);
+
 /* row_ids[i] = i / num_hots, nnz = batch_size * num_hots. */
 int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
                                   int idx_type, cuembed_stream_t stream);
@@ -152,6 +174,50 @@ int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
                         const void* transpose_weights, int skip_grad_init,
                         void* grad_embedding, void* inverse_mapping,
                         char* work, size_t* lwork, cuembed_stream_t stream);
+
+/*
+ * Fused backward + sparse optimizer step (new; the reference lists "optimizer"
+ * as a future kernel type, README.md:119).  Same inputs as cuembed_backward
+ * with full-table indexing (transpose_indices are table rows; no compressed
+ * indices needed), but instead of writing a gradient the finished sum g of
+ * every touched row is applied to `params` [rows, embed_width] (dtype) in
+ * place, each operation rounded separately in fp32:
+ *   CUEMBED_OPT_SGD      p <- p - lr * g
+ *   CUEMBED_OPT_ADAGRAD  s <- s + g * g;  p <- p - (lr * g) / (sqrt(s) + eps)
+ * with `state` = s [rows, embed_width] fp32 (ADAGRAD only).  Rows that receive
+ * no gradient are not touched.  Deterministic like cuembed_backward.  Two-call
+ * workspace protocol.
+ */
+#define CUEMBED_OPT_NONE 0
+#define CUEMBED_OPT_SGD 1
+#define CUEMBED_OPT_ADAGRAD 2
+int cuembed_backward_update(const void* grad_y, int dtype, int embed_width,
+                            int nnz, int idx_type,
+                            const void* transpose_indices,
+                            const void* transpose_sample_ids,
+                            const void* transpose_weights, int optimizer,
+                            float lr, float eps, void* params, float* state,
+                            char* work, size_t* lwork, cuembed_stream_t stream);
+
+/*
+ * Experimental hot-row path of the backward: the interiors of
+ * very long runs are summed sample tile by sample tile through shared memory
+ * (TMA bulk loads) instead of one grad_y row gather per nonzero.  Results are
+ * the same sums in a different, still fixed, association order.  OFF by default
+ * (measured slower end to end on B200); process-wide switch, returns the
+ * previous setting.  The workspace size of cuembed_backward_ws depends on it.
+ */
+int cuembed_set_backward_hot_path(int enable);
+
+/*
+ * Introspection for tests and benchmarks: byte offset, inside the workspace of
+ * cuembed_backward_ws for this problem shape, of two int32 counters that the
+ * call leaves behind: {number of hot units, largest sample id of a hot unit}
+ * (the hot-row path of the backward).  *offset = (size_t)-1 when
+ * that path is switched off for the shape.
+ */
+int cuembed_backward_ws_hot_offset(int dtype, int embed_width, int nnz,
+                                   int idx_type, size_t* offset);
 
 /*
  * Row-sharded multi-GPU mode (new: the reference is single-GPU, README.md:110).

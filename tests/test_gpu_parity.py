@@ -295,6 +295,227 @@ def test_backward_long_runs_and_power_law(cuda_lib, oracle, dt):
     assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, "single run")
 
 
+def _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped):
+    """EmbeddingBackward with explicit workspace; also returns the number of
+    hot units the call found (-1: hot-row path off for the shape)."""
+    dt = gh.TORCH_DT[p.dt]
+    num_rows = (int(remapped[-1].item()) + 1) if p.compressed else p.num_categories
+    grad = torch.full((num_rows, p.width), float("nan"), dtype=dt, device=gh.DEV)
+    inv = (torch.full((num_rows,), -1, dtype=t_idx.dtype, device=gh.DEV)
+           if p.compressed else None)
+    before = ce.set_backward_hot_path(True)  # experimental path, off by default
+    try:
+        work = torch.empty(ce.backward_workspace_bytes(dt, p.width, p.nnz, t_idx.dtype),
+                           dtype=torch.uint8, device=gh.DEV)
+        ce.EmbeddingBackward(gh.to_dev(p.grad_y), p.width, num_rows, p.nnz, t_idx, t_sid,
+                             remapped, t_w, False, grad, inv, work=work)
+        torch.cuda.synchronize()
+        n_hot = ce.backward_hot_units(work, dt, p.width, p.nnz, t_idx.dtype)
+    finally:
+        ce.set_backward_hot_path(before)
+    return gh.to_host(grad), (inv.cpu().numpy() if inv is not None else None), n_hot
+
+
+HOT_CASES = [
+    # width, dtype, weighted, compressed, index type
+    (32, F32, False, True, np.int32),     # 128-byte rows: 4 rows per warp step
+    (128, F16, True, True, np.int32),     # 256-byte rows: 2 rows per warp step
+    (256, F16, False, True, np.int32),    # the headline row shape
+    (256, BF16, True, False, np.int64),   # full gradient, 64-bit indices
+    (128, F32, True, True, np.int64),     # 512-byte fp32 rows
+    (512, F16, False, True, np.int32),    # 1 KB rows: 2 vectors per lane
+    (512, F32, True, True, np.int32),     # 2 KB rows: 4 vectors per lane
+    (1024, F16, False, False, np.int32),  # 2 KB 16-bit rows: 2 units per warp
+    (48, F16, False, True, np.int32),     # 96-byte rows: 6 of 8 lanes
+]
+
+
+@pytest.mark.parametrize("case", HOT_CASES, ids=lambda c: f"w{c[0]}-dt{c[1]}-{'w' if c[2] else 'u'}")
+def test_backward_hot_rows(cuda_lib, oracle, case):
+    """Batches in which a few dozen rows receive thousands of lookups each: the
+    interiors of those runs go through the sample-tile kernel (hot units > 0 is
+    asserted), everything else through the chunk walker.  Integer gradients and
+    power-of-two weights: every partial sum is exact in fp32, so the result
+    must equal the fp32-accumulating oracle whatever the association."""
+    width, dt, weighted, compressed, it = case
+    p = Problem(12288, width, 12, "sum", weighted=weighted, compressed=compressed, dt=dt,
+                num_categories=2500, alpha=1.15, seed=41, index_dtype=it)
+    rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
+    c = p.cpu_transpose(oracle)
+    assert np.array_equal(t_sid.cpu().numpy(), c[2])
+    (c_grad, c_inv), _ = p.cpu_backward(oracle, *c[1:], acc_f32=True)
+    g_grad, g_inv, n_hot = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
+    assert n_hot > 0, "the hot-row path did not engage"
+    touched = np.zeros(c_grad.shape[0], bool)
+    touched[c[4] if compressed else c[1]] = True
+    assert value_equal(raw_rows(g_grad, touched), raw_rows(c_grad, touched)), \
+        _diff(raw_rows(g_grad, touched), raw_rows(c_grad, touched), f"hot backward n_hot={n_hot}")
+    if compressed:
+        assert np.array_equal(g_inv, c_inv)
+    # the default path (chunk walker only) gives the same values
+    g2, _, _ = gh.gpu_backward(p, t_idx, t_sid, t_w, remapped)
+    assert value_equal(g2, g_grad)
+
+
+def raw_rows(a, mask):
+    if isinstance(a, Bf16):
+        return Bf16(a.bits[mask])
+    return a[mask]
+
+
+def test_backward_hot_rows_unsorted_samples_and_concat(cuda_lib, oracle):
+    """The sample-tile kernel needs ascending sample ids inside a run; a caller
+    may pass them in any order (the reference only asks for grouped indices,
+    cuembed/README.md).  Runs whose sample ids are not ascending, and runs that
+    are too sparse in sample space (concat: sample id = lookup position), must
+    stay on the chunk walker and still give the right sums."""
+    p = Problem(12288, 64, 12, "sum", weighted=True, compressed=True, dt=F32,
+                num_categories=2500, alpha=1.15, seed=43)
+    rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
+    c = p.cpu_transpose(oracle)
+    # reverse the (sample id, weight) order inside every run
+    keys = c[1]
+    starts = np.flatnonzero(np.r_[True, keys[1:] != keys[:-1]])
+    ends = np.r_[starts[1:], keys.size]
+    perm = np.concatenate([np.arange(e - 1, s - 1, -1) for s, e in zip(starts, ends)])
+    r_sid = np.ascontiguousarray(c[2][perm])
+    r_w = np.ascontiguousarray(c[3][perm])
+    (c_grad, c_inv), _ = p.cpu_backward(oracle, c[1], r_sid, r_w, c[4], acc_f32=True)
+    g_grad, g_inv, n_hot = _backward_with_hot_count(
+        p, t_idx, gh.to_dev(r_sid), gh.to_dev(r_w), remapped)
+    assert n_hot == 0, "descending sample ids must not be treated as hot units"
+    assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, "reversed runs")
+    assert np.array_equal(g_inv, c_inv)
+    # concat: every lookup is its own "sample"
+    pc = Problem(4096, 64, 8, "concat", compressed=True, dt=F16,
+                 num_categories=300, alpha=1.15, seed=44)
+    rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(pc)
+    cc = pc.cpu_transpose(oracle)
+    (c_grad, c_inv), _ = pc.cpu_backward(oracle, *cc[1:], acc_f32=True)
+    g_grad, g_inv, n_hot = _backward_with_hot_count(pc, t_idx, t_sid, t_w, remapped)
+    assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, f"concat n_hot={n_hot}")
+    assert np.array_equal(g_inv, c_inv)
+
+
+def test_backward_hot_rows_real_valued_and_deterministic(cuda_lib, oracle):
+    """Real-valued gradients through the hot-row path: within 1e-5 of sum|terms|
+    of the sequential fp32 oracle (north_star tolerance for a different
+    accumulation order), and bit-identical from run to run although hot units
+    are registered in arbitrary order."""
+    rng = np.random.default_rng(45)
+    p = Problem(12288, 256, 12, "sum", weighted=True, compressed=True, dt=F32,
+                num_categories=2500, alpha=1.15, seed=46)
+    p.grad_y = rng.standard_normal((p.batch, p.width)).astype(np.float32)
+    p.weights = rng.random(p.nnz).astype(np.float32)
+    rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
+    c = p.cpu_transpose(oracle)
+    (c_grad, _), num_rows = p.cpu_backward(oracle, *c[1:])
+    g_grad, _, n_hot = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
+    assert n_hot > 0
+    l1 = np.zeros((num_rows, p.width))
+    np.add.at(l1, c[4], np.abs(p.grad_y.astype(np.float64)[c[2]] *
+                               c[3].astype(np.float64)[:, None]))
+    rel = np.abs(g_grad.astype(np.float64) - c_grad) / np.maximum(l1, 1e-30)
+    assert np.max(rel) <= 1e-5, float(np.max(rel))
+    for _ in range(3):
+        g2, _, _ = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
+        assert bits_equal(g2, g_grad)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_forward_multi_table(cuda_lib, oracle, dt):
+    """cuembed_forward_multi: 35 tables (two launches of
+    <= 32) with different row counts, batch sizes, fixed hotness or CSR bags and
+    sum or mean, pooled into one [batch, tables * width] activation matrix.
+    Every table's slice must be bit-identical to the oracle's forward of that
+    table (the same bar as the single-table call)."""
+    n_tables, width, max_batch = 35, 32, 300
+    rng = np.random.default_rng(61)
+    probs = []
+    for t in range(n_tables):
+        csr = bool(t % 3 == 1)
+        mode = "mean" if t % 4 == 2 else "sum"
+        batch = max_batch if t % 5 else int(rng.integers(1, max_batch))
+        probs.append(Problem(batch, width, int(rng.integers(1, 20)), mode, csr=csr,
+                             weighted=True, dt=dt, index_dtype=np.int64,
+                             num_categories=int(rng.integers(50, 5000)), alpha=1.05,
+                             seed=100 + t))
+    tdt = gh.TORCH_DT[dt]
+    out = torch.full((max_batch, n_tables * width), float("nan"), dtype=tdt, device=gh.DEV)
+    rets = [out[:p.batch, t * width:(t + 1) * width] for t, p in enumerate(probs)]
+    ce.EmbeddingForwardMulti(
+        [gh.to_dev(p.table) for p in probs], width,
+        [gh.to_dev(p.indices) for p in probs],
+        [gh.to_dev(p.offsets.astype(np.int32)) if p.csr else None for p in probs],
+        [gh.to_dev(p.weights) for p in probs],
+        [p.batch for p in probs], [p.num_hots for p in probs],
+        [int(p.mode) for p in probs], rets, out_row_stride=n_tables * width)
+    torch.cuda.synchronize()
+    for t, p in enumerate(probs):
+        if p.mode == MEAN:
+            # weighted mean is not defined by the CPU reference
+            # (utils/include/embedding_lookup_cpu.hpp:51): compare with the
+            # single-table GPU call, which test_mixed_output_type_and_weighted_mean pins
+            want = gh.gpu_forward(p)
+        else:
+            want = p.cpu_forward(oracle)
+        got = gh.to_host(rets[t].contiguous())
+        assert bits_equal(got, want), _diff(got, want, f"table {t}")
+    # rows below a shorter batch stay untouched
+    for t, p in enumerate(probs):
+        if p.batch < max_batch:
+            tail = out[p.batch:, t * width:(t + 1) * width]
+            assert bool(torch.isnan(tail.float()).all())
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("opt", ["sgd", "adagrad"])
+def test_backward_fused_optimizer_step(cuda_lib, oracle, dt, opt):
+    """cuembed_backward_update: the row sums of the backward
+    applied to the table in place.  The reference has no such kernel
+    (README.md:119 lists it as future work), so the yardstick is the backward
+    oracle's row sums pushed through a numpy float32 restatement of the update,
+    one rounding per operation, which the kernel must match bit for bit;
+    untouched rows must keep their bits."""
+    p = Problem(6000, 96, 10, "sum", weighted=True, dt=dt, num_categories=3000,
+                alpha=1.15, seed=51)
+    rows, t_idx, t_sid, t_w, _ = gh.gpu_transpose(p)
+    c = p.cpu_transpose(oracle)
+    # exact row sums (integer gradients, power-of-two weights)
+    g = np.zeros((p.num_categories, p.width))
+    np.add.at(g, c[1], to_f32(p.grad_y).astype(np.float64)[c[2]] *
+              to_f32(c[3]).astype(np.float64)[:, None])
+    g32 = g.astype(np.float32)
+    assert np.array_equal(g32.astype(np.float64), g)
+    touched = np.zeros(p.num_categories, bool)
+    touched[c[1]] = True
+    lr, eps = np.float32(0.01), np.float32(1e-8)
+    p32 = to_f32(p.table)
+    table = gh.to_dev(p.table)
+    state = None
+    if opt == "sgd":
+        want32 = p32 - lr * g32
+    else:
+        rng = np.random.default_rng(52)
+        s0 = rng.random((p.num_categories, p.width), dtype=np.float32)
+        state = torch.from_numpy(s0.copy()).to(gh.DEV)
+        s1 = s0 + g32 * g32
+        want32 = p32 - (lr * g32) / (np.sqrt(s1) + eps)
+    want = cast_elems(np.where(touched[:, None], want32, p32), dt)
+    ce.EmbeddingBackwardUpdate(gh.to_dev(p.grad_y), p.width, p.nnz, t_idx, t_sid, t_w,
+                               ce.OPT_SGD if opt == "sgd" else ce.OPT_ADAGRAD,
+                               float(lr), table, state=state, eps=float(eps))
+    torch.cuda.synchronize()
+    got = gh.to_host(table)
+    # untouched rows keep their bits; touched rows match the restatement
+    assert bits_equal(raw_rows(got, ~touched), raw_rows(p.table, ~touched))
+    assert bits_equal(raw_rows(got, touched), raw_rows(want, touched)), \
+        _diff(raw_rows(got, touched), raw_rows(want, touched), f"fused {opt}")
+    if state is not None:
+        want_s = np.where(touched[:, None], s1, s0)
+        assert np.array_equal(state.cpu().numpy(), want_s)
+
+
 def test_backward_skip_grad_init_leaves_other_rows(cuda_lib, oracle):
     """skip_grad_init: rows without a gradient keep their content; rows with a
     gradient are overwritten (documented in include/cuembed_b200.h)."""
