@@ -125,23 +125,94 @@ __device__ __forceinline__ void StorePartial(float* dst, const float* acc) {
   }
 }
 
-// One element of the fused optimizer step.  Every operation is rounded
-// separately (no FMA contraction) so a numpy float32 restatement reproduces it
-// bit for bit:  SGD      p <- p - lr * g
-//               Adagrad  s <- s + g * g;  p <- p - (lr * g) / (sqrt(s) + eps)
-__device__ __forceinline__ float OptStep(int kind, float lr, float eps, float p,
-                                         float g, float* state) {
-  if (kind == CUEMBED_OPT_ADAGRAD) {
-    const float s = __fadd_rn(*state, __fmul_rn(g, g));
-    *state = s;
-    return __fsub_rn(
-        p, __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(__fsqrt_rn(s), eps)));
+// ---- fused optimizer step ---------------------------------------------------
+// SGD is a pure "add -lr * g to the row": it goes to the L2 atomic unit as a
+// vector reduction (REDG.E.ADD.F16x8 / BF16x8 / F32x4), fire and forget, so the
+// SM never waits for the cold table row (a read-modify-write in the SM was
+// measured 1.9x slower: every run end waited for DRAM).  Each table row is
+// updated by exactly one reduction (one run per row), so the result does not
+// depend on timing:
+//     p <- p (+) round_T(-(lr * g))      (+) = one add in the table's type, rn
+// (fp32 tables: p - lr * g, subnormal results flushed to zero by the unit).
+// Adagrad needs sqrt of the NEW state and stays a read-modify-write:
+//     s <- s + g * g;  p <- round_T(p - (lr * g) / (sqrt(s) + eps))
+// every operation rounded separately in fp32, so a numpy float32 restatement
+// reproduces it bit for bit.
+template <typename T, int NW>
+__device__ __forceinline__ void RedAddWords(void* addr, const uint32_t* w) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (NW == 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr),
+                   "f"(__uint_as_float(w[0])), "f"(__uint_as_float(w[1])),
+                   "f"(__uint_as_float(w[2])), "f"(__uint_as_float(w[3]))
+                   : "memory");
+    else if constexpr (NW == 2)
+      asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(addr),
+                   "f"(__uint_as_float(w[0])), "f"(__uint_as_float(w[1]))
+                   : "memory");
+    else
+      asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr),
+                   "f"(__uint_as_float(w[0]))
+                   : "memory");
+  } else if constexpr (Elem<T>::kCode == CUEMBED_F16) {
+    if constexpr (NW == 4)
+      asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(
+                       addr),
+                   "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                   : "memory");
+    else if constexpr (NW == 2)
+      asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1,%2};" ::"l"(addr),
+                   "r"(w[0]), "r"(w[1])
+                   : "memory");
+    else
+      asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(w[0])
+                   : "memory");
+  } else {
+    if constexpr (NW == 4)
+      asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(
+                       addr),
+                   "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                   : "memory");
+    else if constexpr (NW == 2)
+      asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1,%2};" ::"l"(addr),
+                   "r"(w[0]), "r"(w[1])
+                   : "memory");
+    else
+      asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(addr),
+                   "r"(w[0])
+                   : "memory");
   }
-  return __fsub_rn(p, __fmul_rn(lr, g));
 }
 
-// In-place update of NE consecutive elements of table row `row` with the
-// finished gradient sums g[NE] (one V-byte vector of the row per lane).
+// One element through the same unit (fix-up kernel: runs that cross chunks).
+template <typename T>
+__device__ __forceinline__ void RedAddOne(T* addr, float v) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+  } else if constexpr (Elem<T>::kCode == CUEMBED_F16) {
+    const __half h = __float2half_rn(v);
+    asm volatile("red.global.add.noftz.f16 [%0], %1;" ::"l"(addr),
+                 "h"(*reinterpret_cast<const unsigned short*>(&h))
+                 : "memory");
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    asm volatile("red.global.add.noftz.bf16 [%0], %1;" ::"l"(addr),
+                 "h"(*reinterpret_cast<const unsigned short*>(&h))
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ float AdagradStep(float lr, float eps, float p,
+                                             float g, float* state) {
+  const float s = __fadd_rn(*state, __fmul_rn(g, g));
+  *state = s;
+  return __fsub_rn(p,
+                   __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(__fsqrt_rn(s), eps)));
+}
+
+// Update of NE consecutive elements of table row `row` with the finished
+// gradient sums g[NE] (one V-byte vector of the row per lane).  old_vec is the
+// current content of the vector (Adagrad only).
 template <typename T, int V, int NE>
 __device__ __forceinline__ void ApplyUpdateVec(
     const BwdArgs& a, char* table_row, int64_t row, int64_t elem_off,
@@ -150,14 +221,24 @@ __device__ __forceinline__ void ApplyUpdateVec(
   constexpr int NW = V / 4;
   VecT* pv = reinterpret_cast<VecT*>(table_row + elem_off * sizeof(T));
   uint32_t w[NW];
+  if (a.opt_kind == CUEMBED_OPT_SGD) {
+    const float neg_lr = -a.opt_lr;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      float f[Elem<T>::kPerWord];
+#pragma unroll
+      for (int k = 0; k < Elem<T>::kPerWord; ++k)
+        f[k] = __fmul_rn(neg_lr, g[i * Elem<T>::kPerWord + k]);
+      w[i] = Elem<T>::FloatToWord(f);
+    }
+    RedAddWords<T, NW>(pv, w);
+    return;
+  }
   Unpack32(old_vec, w);
   float st[NE];
-  float* sp = nullptr;
-  if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
-    sp = a.opt_state + row * a.width + elem_off;
+  float* sp = a.opt_state + row * a.width + elem_off;
 #pragma unroll
-    for (int e = 0; e < NE; ++e) st[e] = sp[e];
-  }
+  for (int e = 0; e < NE; ++e) st[e] = sp[e];
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     float f[Elem<T>::kPerWord];
@@ -165,22 +246,25 @@ __device__ __forceinline__ void ApplyUpdateVec(
 #pragma unroll
     for (int k = 0; k < Elem<T>::kPerWord; ++k) {
       const int e = i * Elem<T>::kPerWord + k;
-      f[k] = OptStep(a.opt_kind, a.opt_lr, a.opt_eps, f[k], g[e], &st[e]);
+      f[k] = AdagradStep(a.opt_lr, a.opt_eps, f[k], g[e], &st[e]);
     }
     w[i] = Elem<T>::FloatToWord(f);
   }
   VecT out;
   Pack32(w, &out);
   *pv = out;
-  if (sp != nullptr) StorePartial<NE>(sp, st);
+  StorePartial<NE>(sp, st);
 }
 
 }  // namespace cuembed_b200
 #include "backward_hot.cuh"
 namespace cuembed_b200 {
 
+// FUSED_OPT: CUEMBED_OPT_NONE (write the gradient), _SGD (vector reductions
+// into the table, nothing read), _ADAGRAD (old table rows requested with the
+// gradient rows).
 template <typename T, int V, typename IdxT, bool WEIGHTED, int UNROLL,
-          bool FUSED_OPT>
+          int FUSED_OPT>
 __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     BwdSegReduceKernel(const BwdArgs a) {
   using VecT = typename VecBits<V>::type;
@@ -273,6 +357,17 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     const bool end =
         lane_g < cnt && ((i == a.nnz - 1) || (n_knext != key));
     if (r + 1 < a.rounds) request(r + 1);
+    // Fused optimizer: the table rows this round will update are cold (DRAM);
+    // ask for them now so that the read-modify-write at the run end finds them
+    // in L2 (without this every batch with a run end waited for DRAM).
+    if constexpr (FUSED_OPT == CUEMBED_OPT_ADAGRAD) {
+      if (end && blockIdx.y == 0) {
+        const char* trow_ptr = static_cast<const char*>(a.grad) +
+                               GradRowOffset<IdxT>(key, row_bytes);
+        for (uint32_t off = 0; off < row_bytes; off += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(trow_ptr + off));
+      }
+    }
     const unsigned endsw = __ballot_sync(kFull, end);
     const int cnt_max = (G == 32) ? cnt : __reduce_max_sync(kFull, cnt);
 
@@ -280,7 +375,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     for (int jb = 0; jb < cnt_max; jb += UNROLL) {
       VecT vals[UNROLL];
       T wv[UNROLL];
-      VecT pold[FUSED_OPT ? UNROLL : 1];
+      VecT pold[FUSED_OPT == CUEMBED_OPT_ADAGRAD ? UNROLL : 1];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         const int src = (jb + u) & (G - 1);
@@ -306,7 +401,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
         // Fused optimizer: the table row that a run ending at this position
         // will update is requested together with the gradient rows, so the
         // read-modify-write does not wait for DRAM at every run end.
-        if constexpr (FUSED_OPT) {
+        if constexpr (FUSED_OPT == CUEMBED_OPT_ADAGRAD) {
           const IdxT kr = ShflIdx<IdxT>(key, src, G);
           pold[u] = VecT();
           if (active && jb + u < G && ((endsw >> (gl0 + jb + u)) & 1u) != 0u)
@@ -355,13 +450,13 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
             } else if (active) {
               char* out_row = static_cast<char*>(a.grad) +
                               GradRowOffset<IdxT>(krow, row_bytes);
-              if constexpr (!FUSED_OPT)
+              if constexpr (FUSED_OPT == CUEMBED_OPT_NONE)
                 StoreFloatsAs<NE>(out_row, static_cast<int64_t>(v) * NE,
                                   Elem<T>::kCode, acc);
               else
                 ApplyUpdateVec<T, V, NE>(a, out_row, static_cast<int64_t>(krow),
                                          static_cast<int64_t>(v) * NE, acc,
-                                         pold[FUSED_OPT ? u : 0]);
+                                         pold[FUSED_OPT == CUEMBED_OPT_ADAGRAD ? u : 0]);
             }
             if (a.inverse_mapping != nullptr && lane_g == 0 &&
                 blockIdx.y == 0) {
@@ -522,17 +617,15 @@ __global__ void __launch_bounds__(kCtaThreads)
   }
   const long long row = a.meta_row[c0 * 2 + 1];
   T* dst = static_cast<T*>(a.grad) + row * a.width + col;
-  if (a.opt_kind != CUEMBED_OPT_NONE) {
-    // fused optimizer step: the finished sum updates the table element
-    float st = 0.f;
-    float* sp = nullptr;
-    if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
-      sp = a.opt_state + row * a.width + col;
-      st = *sp;
-    }
-    acc = OptStep(a.opt_kind, a.opt_lr, a.opt_eps, Elem<T>::ToFloat(*dst), acc,
-                  &st);
-    if (sp != nullptr) *sp = st;
+  if (a.opt_kind == CUEMBED_OPT_SGD) {
+    RedAddOne<T>(dst, __fmul_rn(-a.opt_lr, acc));
+    return;
+  }
+  if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
+    float* sp = a.opt_state + row * a.width + col;
+    float st = *sp;
+    acc = AdagradStep(a.opt_lr, a.opt_eps, Elem<T>::ToFloat(*dst), acc, &st);
+    *sp = st;
   }
   StoreOneAs<T>(dst, acc);
 }
@@ -672,11 +765,14 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
     }
   }
   dim3 grid(a.num_ctas, col_tiles);
-  if (a.opt_kind != CUEMBED_OPT_NONE)
-    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4, true>
+  if (a.opt_kind == CUEMBED_OPT_ADAGRAD)
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4, CUEMBED_OPT_ADAGRAD>
+        <<<grid, kBwdThreads, 0, stream>>>(a);  // 4: room for the old rows
+  else if (a.opt_kind == CUEMBED_OPT_SGD)
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8, CUEMBED_OPT_SGD>
         <<<grid, kBwdThreads, 0, stream>>>(a);
   else
-    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8, false>
+    BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 8, CUEMBED_OPT_NONE>
         <<<grid, kBwdThreads, 0, stream>>>(a);
   const int wtiles = (a.width + kCtaThreads - 1) / kCtaThreads;
   const int groups = a.num_chunks / kFixGroup;

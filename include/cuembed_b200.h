@@ -181,12 +181,17 @@ int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
  * with full-table indexing (transpose_indices are table rows; no compressed
  * indices needed), but instead of writing a gradient the finished sum g of
  * every touched row is applied to `params` [rows, embed_width] (dtype) in
- * place, each operation rounded separately in fp32:
- *   CUEMBED_OPT_SGD      p <- p - lr * g
- *   CUEMBED_OPT_ADAGRAD  s <- s + g * g;  p <- p - (lr * g) / (sqrt(s) + eps)
- * with `state` = s [rows, embed_width] fp32 (ADAGRAD only).  Rows that receive
- * no gradient are not touched.  Deterministic like cuembed_backward.  Two-call
- * workspace protocol.
+ * place:
+ *   CUEMBED_OPT_SGD      p <- p (+) round(-(lr * g)): the update is rounded to
+ *                        the table's type and added by the L2 reduction unit
+ *                        (one vector red per 16 bytes, nothing is read back
+ *                        into the SM); fp32 tables: p - lr * g with subnormal
+ *                        results flushed to zero.  One reduction per row, so
+ *                        the result is deterministic.
+ *   CUEMBED_OPT_ADAGRAD  s <- s + g * g;  p <- p - (lr * g) / (sqrt(s) + eps),
+ *                        every operation rounded separately in fp32, with
+ *                        `state` = s [rows, embed_width] fp32.
+ * Rows that receive no gradient are not touched.  Two-call workspace protocol.
  */
 #define CUEMBED_OPT_NONE 0
 #define CUEMBED_OPT_SGD 1

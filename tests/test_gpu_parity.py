@@ -473,10 +473,10 @@ def test_forward_multi_table(cuda_lib, oracle, dt):
 def test_backward_fused_optimizer_step(cuda_lib, oracle, dt, opt):
     """cuembed_backward_update: the row sums of the backward
     applied to the table in place.  The reference has no such kernel
-    (README.md:119 lists it as future work), so the yardstick is the backward
-    oracle's row sums pushed through a numpy float32 restatement of the update,
-    one rounding per operation, which the kernel must match bit for bit;
-    untouched rows must keep their bits."""
+    (README.md:119 lists it as future work), so the yardstick is the exact row
+    sums (integer gradients) pushed through a numpy restatement of the update
+    as documented in include/cuembed_b200.h, one rounding per operation, which
+    the kernel must match bit for bit; untouched rows must keep their bits."""
     p = Problem(6000, 96, 10, "sum", weighted=True, dt=dt, num_categories=3000,
                 alpha=1.15, seed=51)
     rows, t_idx, t_sid, t_w, _ = gh.gpu_transpose(p)
@@ -494,14 +494,19 @@ def test_backward_fused_optimizer_step(cuda_lib, oracle, dt, opt):
     table = gh.to_dev(p.table)
     state = None
     if opt == "sgd":
-        want32 = p32 - lr * g32
+        # p (+) round_T(-(lr * g)): one add in the table's type (the L2 atomic
+        # unit does it); float64 holds the exact sum of two T values
+        upd = cast_elems((-lr) * g32, dt)
+        want_t = to_f32(p.table).astype(np.float64) + to_f32(upd).astype(np.float64)
+        want_touched = (want_t.astype(np.float16) if dt == F16 else
+                        cast_elems(want_t.astype(np.float32), dt))
     else:
         rng = np.random.default_rng(52)
         s0 = rng.random((p.num_categories, p.width), dtype=np.float32)
         state = torch.from_numpy(s0.copy()).to(gh.DEV)
         s1 = s0 + g32 * g32
-        want32 = p32 - (lr * g32) / (np.sqrt(s1) + eps)
-    want = cast_elems(np.where(touched[:, None], want32, p32), dt)
+        want_touched = cast_elems(p32 - (lr * g32) / (np.sqrt(s1) + eps), dt)
+    want = want_touched
     ce.EmbeddingBackwardUpdate(gh.to_dev(p.grad_y), p.width, p.nnz, t_idx, t_sid, t_w,
                                ce.OPT_SGD if opt == "sgd" else ce.OPT_ADAGRAD,
                                float(lr), table, state=state, eps=float(eps))
