@@ -89,6 +89,70 @@ void EmbeddingBackward(const GradT* grad_y, const int embed_width,
       "EmbeddingBackward");
 }
 
+// ---- additions of the B200 build (no counterpart in the reference; its README
+// lists "optimizer" kernels and "multiple tables" as future work, :110,119) ----
+
+enum class SparseOptimizer { kSgd = CUEMBED_OPT_SGD, kAdagrad = CUEMBED_OPT_ADAGRAD };
+
+// Backward fused with a sparse optimizer step on the touched rows of `params`
+// (include/cuembed_b200.h: cuembed_backward_update).  transpose_indices are
+// table rows; `state` is the fp32 Adagrad accumulator (nullptr for SGD).
+// Scratch through the reference's work / lwork two-call protocol.
+template <typename GradT, typename IndexT>
+void EmbeddingBackwardUpdate(const GradT* grad_y, const int embed_width,
+                             const int nnz, const IndexT* transpose_indices,
+                             const IndexT* transpose_sample_ids,
+                             const GradT* transpose_weights,
+                             const SparseOptimizer optimizer, const float lr,
+                             const float eps, GradT* params, float* state,
+                             char* work, size_t* lwork,
+                             const cudaStream_t stream = 0) {
+  b200_detail::CheckCode(
+      cuembed_backward_update(grad_y, b200_detail::DTypeCode<GradT>::value,
+                              embed_width, nnz,
+                              b200_detail::ITypeCode<IndexT>::value,
+                              transpose_indices, transpose_sample_ids,
+                              transpose_weights, static_cast<int>(optimizer),
+                              lr, eps, params, state, work, lwork,
+                              reinterpret_cast<cuembed_stream_t>(stream)),
+      "EmbeddingBackwardUpdate");
+}
+
+// Pooled lookups into `num_tables` tables of one row shape in one launch
+// (cuembed_forward_multi).  HOST arrays of per-table device pointers / sizes;
+// offsets / weights / modes may be nullptr (fixed hotness / unweighted / sum).
+template <typename InputT, typename OutputT, typename IndexT, typename OffsetT>
+void EmbeddingForwardMulti(const int num_tables, const InputT* const* params,
+                           const int embed_width, const IndexT* const* indices,
+                           const OffsetT* const* offsets,
+                           const GetElemT<InputT>* const* weights,
+                           const int* batch_sizes, const int* num_hots,
+                           const CombineMode* modes, OutputT* const* rets,
+                           const long long out_row_stride = 0,
+                           const cudaStream_t stream = 0) {
+  int mode_codes[64];
+  int* mc = nullptr;
+  if (modes != nullptr) {
+    CUEMBED_ASSERT(num_tables <= 64);
+    for (int t = 0; t < num_tables; ++t)
+      mode_codes[t] = b200_detail::ModeCode(modes[t]);
+    mc = mode_codes;
+  }
+  b200_detail::CheckCode(
+      cuembed_forward_multi(
+          num_tables, reinterpret_cast<const void* const*>(params),
+          b200_detail::DTypeCode<GetElemT<InputT>>::value, embed_width,
+          reinterpret_cast<const void* const*>(indices),
+          b200_detail::ITypeCode<IndexT>::value,
+          reinterpret_cast<const void* const*>(offsets),
+          b200_detail::ITypeCode<OffsetT>::value,
+          reinterpret_cast<const void* const*>(weights), batch_sizes, num_hots,
+          mc, reinterpret_cast<void* const*>(rets),
+          b200_detail::DTypeCode<GetElemT<OutputT>>::value, out_row_stride,
+          reinterpret_cast<cuembed_stream_t>(stream)),
+      "EmbeddingForwardMulti");
+}
+
 }  // namespace cuembed
 
 #endif  // CUEMBED_INCLUDE_EMBEDDING_LOOKUP_CUH_

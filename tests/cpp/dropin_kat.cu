@@ -142,6 +142,39 @@ int RunAll(const char* tag) {
   failures += !Equal(grad, {15, 18, 21, 24, 1, 2, 3, 4, 15.5, 19, 22.5, 26},
                      "backward compressed weighted");
   failures += !EqualI(inv, {0, 1, 3}, "inverse mapping");
+
+  // ---- additions of the B200 build: fused SGD step and multi-table forward
+  // table rows 0, 1, 3 receive the "backward full" sums above; lr = 0.5
+  ElemT* tab2 = Managed<ElemT>(table);
+  size_t lw_upd = 0;
+  cuembed::EmbeddingBackwardUpdate<ElemT, IndexT>(
+      grad_y, 4, 4, b_idx, b_sid, no_weights, cuembed::SparseOptimizer::kSgd, 0.5f,
+      0.f, tab2, nullptr, nullptr, &lw_upd);
+  char* work_upd = nullptr;
+  CUDA_OK(cudaMalloc(&work_upd, lw_upd));
+  cuembed::EmbeddingBackwardUpdate<ElemT, IndexT>(
+      grad_y, 4, 4, b_idx, b_sid, no_weights, cuembed::SparseOptimizer::kSgd, 0.5f,
+      0.f, tab2, nullptr, work_upd, &lw_upd);
+  CUDA_OK(cudaDeviceSynchronize());
+  failures += !Equal(tab2, {1 - 2.5f, 2 - 3, 3 - 3.5f, 4 - 4, 5 - 0.5f, 6 - 1, 7 - 1.5f,
+                            8 - 2, 9, 10, 11, 12, 13 - 3, 14 - 4, 15 - 5, 16 - 6, 17, 18,
+                            19, 20},
+                     "fused sgd step");
+  ElemT* ret2 = Managed<ElemT>(std::vector<float>(16, -1.f));
+  const ElemT* m_params[2] = {params, params};
+  const IndexT* m_indices[2] = {indices, indices};
+  const int* m_offsets[2] = {nullptr, offsets};
+  const int m_batch[2] = {2, 2};
+  const int m_hots[2] = {2, 0};
+  const CombineMode m_modes[2] = {CombineMode::kSum, CombineMode::kMean};
+  ElemT* m_rets[2] = {ret2, ret2 + 4};  // one [2, 2 * 4] activation matrix
+  const ElemT* const* m_no_weights = nullptr;
+  cuembed::EmbeddingForwardMulti<ElemT, ElemT, IndexT, int>(
+      2, m_params, 4, m_indices, m_offsets, m_no_weights, m_batch, m_hots, m_modes,
+      m_rets, 8);
+  CUDA_OK(cudaDeviceSynchronize());
+  failures += !Equal(ret2, {18, 20, 22, 24, 9, 10, 11, 12, 18, 20, 22, 24, 9, 10, 11, 12},
+                     "multi-table forward");
   std::printf("%s: %s\n", tag, failures == 0 ? "PASS" : "FAIL");
   return failures;
 }
