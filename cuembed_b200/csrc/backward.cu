@@ -534,13 +534,16 @@ __global__ void __launch_bounds__(kCtaThreads)
 
 // Fix-up, level 2: adds, in chunk order, the partials of every run that crosses
 // chunk edges: tail of the chunk where the run starts + heads of the following
-// chunks, whole "through" groups taken from level 1.  The chain length is found
-// first (all threads scan the head kinds), so the loads of the partial rows are
-// independent and issued sixteen at a time.  Every sum has a fixed association.
-// (A warp-per-chunk variant with 8 x 8 loads in flight per lane was measured
-// slower, 38 vs 30 us at C2: fewer resident warps per dependent round trip.)
+// chunks, whole "through" groups taken from level 1.  One small CTA (64
+// threads) per chunk: most chunks have nothing to do or a two-element chain, so
+// what matters is how many of them an SM holds (32 CTAs) while each waits for
+// its three or four dependent round trips; 256-thread CTAs took 30 us at C2,
+// one warp per chunk 38 us.  A thread owns every 64th column, four columns and
+// eight chain elements in flight.  Every sum has a fixed association.
+constexpr int kFixThreads = 64;
+
 template <typename T>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kFixThreads)
     BwdFixupKernel(const BwdArgs a) {
   __shared__ int s_len;
   const int c0 = blockIdx.x;
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(kCtaThreads)
   // chain = chunks c0+1 .. c0+len; the last one has kind "ends".
   if (tid == 0) s_len = 0x7fffffff;
   __syncthreads();
-  for (int base = c0 + 1; base < a.num_chunks; base += kCtaThreads) {
+  for (int base = c0 + 1; base < a.num_chunks; base += kFixThreads) {
     const int c = base + tid;
     if (c < a.num_chunks && a.meta[c * 2 + 0] != kHeadThrough)
       atomicMin(&s_len, c - c0);
@@ -567,67 +570,85 @@ __global__ void __launch_bounds__(kCtaThreads)
   // a "none" head at the end of the chain means the run ended exactly at the
   // chunk edge (cannot happen for a tail, kept as a guard): exclude it.
   if (c0 + len < a.num_chunks && a.meta[(c0 + len) * 2 + 0] == kHeadNone) --len;
-
-  const int col = blockIdx.y * kCtaThreads + tid;
-  if (col >= a.width) return;
-  const float* __restrict__ scratch = a.scratch;
-  const size_t pitch = static_cast<size_t>(2) * a.width;
-  constexpr int kInFlight = 16;
-  float acc = scratch[static_cast<size_t>(c0) * pitch + a.width + col];
   const int end = c0 + len;  // inclusive
   // whole groups inside the "through" part of the chain: [g0, g1)
   int g0 = (c0 + 1 + kFixGroup - 1) / kFixGroup;
   int g1 = (last_through + 1) / kFixGroup;
   if (g1 <= g0) g0 = g1 = 0x3fffffff / kFixGroup;  // none
   const int lead_end = min(end, g0 * kFixGroup - 1);  // singles before the groups
-  int c = c0 + 1;
-  for (; c + kInFlight - 1 <= lead_end; c += kInFlight) {
-    float v[kInFlight];
-#pragma unroll
-    for (int u = 0; u < kInFlight; ++u)
-      v[u] = scratch[static_cast<size_t>(c + u) * pitch + col];
-#pragma unroll
-    for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
-  }
-  for (; c <= lead_end; ++c)
-    acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
-  if (c <= end && g1 > g0) {
-    const float* __restrict__ gp = a.group_part + col;
-    int g = g0;
-    for (; g + kInFlight <= g1; g += kInFlight) {
-      float v[kInFlight];
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u)
-        v[u] = gp[static_cast<size_t>(g + u) * a.width];
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
-    }
-    for (; g < g1; ++g) acc = __fadd_rn(acc, gp[static_cast<size_t>(g) * a.width]);
-    c = g1 * kFixGroup;
-    for (; c + kInFlight - 1 <= end; c += kInFlight) {
-      float v[kInFlight];
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u)
-        v[u] = scratch[static_cast<size_t>(c + u) * pitch + col];
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u) acc = __fadd_rn(acc, v[u]);
-    }
-    for (; c <= end; ++c)
-      acc = __fadd_rn(acc, scratch[static_cast<size_t>(c) * pitch + col]);
-  }
+
+  const size_t pitch = static_cast<size_t>(2) * a.width;
   const long long row = a.meta_row[c0 * 2 + 1];
-  T* dst = static_cast<T*>(a.grad) + row * a.width + col;
-  if (a.opt_kind == CUEMBED_OPT_SGD) {
-    RedAddOne<T>(dst, __fmul_rn(-a.opt_lr, acc));
-    return;
+  constexpr int kCols = 4;
+  constexpr int kRows = 8;
+  for (int cb = tid; cb < a.width; cb += kFixThreads * kCols) {
+    float acc[kCols];
+    bool live[kCols];
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+      live[i] = cb + kFixThreads * i < a.width;
+      acc[i] = live[i] ? a.scratch[static_cast<size_t>(c0) * pitch + a.width + cb +
+                                   kFixThreads * i]
+                       : 0.f;
+    }
+    // acc += rows p[0], p[stride], ... (count rows), in order
+    auto add_rows = [&](const float* __restrict__ p, size_t stride, int count) {
+      int r = 0;
+      for (; r + kRows <= count; r += kRows) {
+        float v[kRows][kCols];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u)
+#pragma unroll
+          for (int i = 0; i < kCols; ++i)
+            v[u][i] = live[i] ? p[static_cast<size_t>(r + u) * stride + kFixThreads * i]
+                              : 0.f;
+#pragma unroll
+        for (int u = 0; u < kRows; ++u)
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) acc[i] = __fadd_rn(acc[i], v[u][i]);
+      }
+      for (; r < count; ++r) {
+        float v[kCols];
+#pragma unroll
+        for (int i = 0; i < kCols; ++i)
+          v[i] = live[i] ? p[static_cast<size_t>(r) * stride + kFixThreads * i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kCols; ++i)
+          if (live[i]) acc[i] = __fadd_rn(acc[i], v[i]);
+      }
+    };
+    int c = c0 + 1;
+    if (lead_end >= c) {
+      add_rows(a.scratch + static_cast<size_t>(c) * pitch + cb, pitch,
+               lead_end - c + 1);
+      c = lead_end + 1;
+    }
+    if (c <= end && g1 > g0) {
+      add_rows(a.group_part + static_cast<size_t>(g0) * a.width + cb,
+               static_cast<size_t>(a.width), g1 - g0);
+      c = g1 * kFixGroup;
+      if (c <= end)
+        add_rows(a.scratch + static_cast<size_t>(c) * pitch + cb, pitch,
+                 end - c + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+      if (!live[i]) continue;
+      T* dst = static_cast<T*>(a.grad) + row * a.width + cb + kFixThreads * i;
+      if (a.opt_kind == CUEMBED_OPT_SGD) {
+        RedAddOne<T>(dst, __fmul_rn(-a.opt_lr, acc[i]));
+        continue;
+      }
+      float val = acc[i];
+      if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
+        float* sp = a.opt_state + row * a.width + cb + kFixThreads * i;
+        float st = *sp;
+        val = AdagradStep(a.opt_lr, a.opt_eps, Elem<T>::ToFloat(*dst), val, &st);
+        *sp = st;
+      }
+      StoreOneAs<T>(dst, val);
+    }
   }
-  if (a.opt_kind == CUEMBED_OPT_ADAGRAD) {
-    float* sp = a.opt_state + row * a.width + col;
-    float st = *sp;
-    acc = AdagradStep(a.opt_lr, a.opt_eps, Elem<T>::ToFloat(*dst), acc, &st);
-    *sp = st;
-  }
-  StoreOneAs<T>(dst, acc);
 }
 
 namespace {
@@ -778,7 +799,7 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   const int groups = a.num_chunks / kFixGroup;
   if (groups > 0)
     BwdGroupKernel<<<dim3(groups, wtiles), kCtaThreads, 0, stream>>>(a);
-  BwdFixupKernel<T><<<dim3(a.num_chunks, wtiles), kCtaThreads, 0, stream>>>(a);
+  BwdFixupKernel<T><<<a.num_chunks, kFixThreads, 0, stream>>>(a);
   CountLaunch(groups > 0 ? 3 : 2);
 }
 
