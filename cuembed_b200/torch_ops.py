@@ -177,6 +177,78 @@ def _(y_grad, transpose_indices, transpose_sample_ids, transpose_weights=None):
             torch.empty((n,), device=y_grad.device, dtype=transpose_indices.dtype))
 
 
+def _backward_update(y_grad, params, state, t_idx, t_sid, t_w, lr, eps, opt):
+    if not params.is_contiguous():
+        raise ValueError("params must be contiguous (it is updated in place)")
+    nnz = t_idx.size(0)
+    if nnz == 0:
+        return
+    w = t_w.contiguous() if t_w is not None else None
+    api.EmbeddingBackwardUpdate(y_grad.contiguous(), params.size(1), nnz, t_idx.contiguous(),
+                                t_sid.contiguous(), w, opt, lr, params, state=state, eps=eps)
+
+
+# Backward fused with the sparse optimizer step (an addition,
+# the reference lists it as future work, README.md:119): the gradient of the
+# touched rows is applied to `params` in place, no gradient tensor exists.
+@torch.library.custom_op("cuembed_pyt::cuembed_embedding_backward_sgd",
+                         mutates_args=("params",), device_types="cuda")
+def cuembed_embedding_backward_sgd(
+        y_grad: torch.Tensor, params: torch.Tensor, transpose_indices: torch.Tensor,
+        transpose_sample_ids: torch.Tensor, transpose_weights: Optional[torch.Tensor],
+        lr: float) -> None:
+    _backward_update(y_grad, params, None, transpose_indices, transpose_sample_ids,
+                     transpose_weights, lr, 0.0, api.OPT_SGD)
+
+
+@cuembed_embedding_backward_sgd.register_fake
+def _(y_grad, params, transpose_indices, transpose_sample_ids, transpose_weights, lr):
+    return None
+
+
+@torch.library.custom_op("cuembed_pyt::cuembed_embedding_backward_adagrad",
+                         mutates_args=("params", "state"), device_types="cuda")
+def cuembed_embedding_backward_adagrad(
+        y_grad: torch.Tensor, params: torch.Tensor, state: torch.Tensor,
+        transpose_indices: torch.Tensor, transpose_sample_ids: torch.Tensor,
+        transpose_weights: Optional[torch.Tensor], lr: float, eps: float) -> None:
+    _backward_update(y_grad, params, state, transpose_indices, transpose_sample_ids,
+                     transpose_weights, lr, eps, api.OPT_ADAGRAD)
+
+
+@cuembed_embedding_backward_adagrad.register_fake
+def _(y_grad, params, state, transpose_indices, transpose_sample_ids,
+      transpose_weights, lr, eps):
+    return None
+
+
+def cuemb_embedding_sgd_step(params, idx, offsets, out_grad, lr: float, weights=None,
+                             mode: str = "sum", optimizer: str = "sgd", state=None,
+                             eps: float = 1e-10) -> None:
+    """One sparse optimizer step of an EmbeddingBag(include_last_offset=True)
+    table given d loss / d output: row ids -> transpose -> fused update, without
+    materialising the gradient (use instead of autograd + torch.optim for the
+    embedding table).  `params` is updated in place."""
+    nnz = idx.size(0)
+    sample_ids = cuembed_extract_row_ids_from_csr(offsets[:-1], nnz)
+    if sample_ids.dtype != idx.dtype:
+        sample_ids = sample_ids.to(idx.dtype)
+    if mode == "mean" and weights is not None:
+        raise ValueError("weighted mean has no backward formula (README.md:117)")
+    w = _coo_weights(mode, offsets, weights, sample_ids, out_grad.dtype)
+    t_idx, t_sid, t_w = cuembed_transpose(sample_ids, idx, w)
+    t_w = None if t_w.numel() == 0 else t_w
+    if optimizer == "sgd":
+        cuembed_embedding_backward_sgd(out_grad, params, t_idx, t_sid, t_w, lr)
+    elif optimizer == "adagrad":
+        if state is None:
+            raise ValueError("adagrad needs an fp32 state tensor shaped like params")
+        cuembed_embedding_backward_adagrad(out_grad, params, state, t_idx, t_sid, t_w,
+                                           lr, eps)
+    else:
+        raise ValueError("optimizer must be 'sgd' or 'adagrad'")
+
+
 # ----------------------------------------------------------------- autograd
 def cuembed_forward(params, idx, offsets, weights, mode="sum"):
     return cuembed_embedding_forward(params, idx, offsets, weights, mode)

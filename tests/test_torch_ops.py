@@ -200,3 +200,52 @@ def test_opcheck_and_compile_tracing(cuda_lib):
     assert torch.allclose(w_ref.grad, w_c.grad, atol=1e-4)
     with torch.no_grad():
         assert torch.allclose(torch.compile(run, backend="aot_eager")(w), run(w))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad"])
+def test_fused_optimizer_step_matches_torch_optim(optimizer):
+    """cuemb_embedding_sgd_step (the fused backward + optimizer op, an addition
+    over the reference example) against nn.EmbeddingBag + torch.optim on the
+    same table: fp32, so one step agrees to rounding (the summation order of the
+    gradient differs: <= 1e-5 relative, north_star tolerance)."""
+    import torch
+    from cuembed_b200.torch_ops import cuemb_embedding, cuemb_embedding_sgd_step
+    torch.manual_seed(5)
+    dev = "cuda:0"
+    rows, width, batch = 2000, 64, 512
+    lens = torch.randint(0, 12, (batch,))
+    offsets = torch.zeros(batch + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lens, 0)
+    nnz = int(offsets[-1])
+    idx = torch.randint(0, rows, (nnz,), dtype=torch.int64)
+    table0 = torch.randn(rows, width)
+    out_grad = torch.randn(batch, width)
+    lr = 0.05
+
+    ref = torch.nn.EmbeddingBag(rows, width, mode="sum", include_last_offset=True).to(dev)
+    with torch.no_grad():
+        ref.weight.copy_(table0)
+    opt = (torch.optim.SGD(ref.parameters(), lr=lr) if optimizer == "sgd" else
+           torch.optim.Adagrad(ref.parameters(), lr=lr, eps=1e-10, initial_accumulator_value=0.0))
+    ref(idx.to(dev), offsets.to(dev)).backward(out_grad.to(dev))
+    opt.step()
+
+    mine = table0.clone().to(dev)
+    state = torch.zeros_like(mine) if optimizer == "adagrad" else None
+    # the forward of the same table first (the step must not disturb it)
+    y = cuemb_embedding(mine, idx.to(dev), offsets.to(dev))
+    assert torch.allclose(y, ref_forward(table0.to(dev), idx.to(dev), offsets.to(dev)), rtol=1e-5, atol=1e-5)
+    cuemb_embedding_sgd_step(mine, idx.to(dev), offsets.to(dev), out_grad.to(dev), lr,
+                             optimizer=optimizer, state=state)
+    torch.cuda.synchronize()
+    assert torch.allclose(mine, ref.weight.detach(), rtol=1e-5, atol=1e-5)
+    untouched = torch.ones(rows, dtype=torch.bool)
+    untouched[idx] = False
+    assert torch.equal(mine[untouched.to(dev)], table0.to(dev)[untouched.to(dev)])
+
+
+def ref_forward(table, idx, offsets):
+    import torch
+    return torch.nn.functional.embedding_bag(idx, table, offsets, mode="sum",
+                                             include_last_offset=True)
