@@ -688,8 +688,12 @@ int BackwardHotPathEnabled() {
 }
 
 bool HotPathShape(int embed_width, int dtype) {
+  RowShape shape;
+  if (!MakeRowShape(embed_width, dtype, &shape)) return false;
   const int64_t row_bytes = static_cast<int64_t>(embed_width) * ElemSize(dtype);
-  return row_bytes % 16 == 0 && row_bytes >= 64 && row_bytes <= 2048;
+  // the tile kernel moves 16-byte vectors: rows the chunk walker cuts into
+  // narrower vectors (fewer than 8 x 16 bytes) stay on the chunk walker
+  return shape.vec_bytes == 16 && row_bytes <= 2048;
 }
 
 BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
@@ -1003,6 +1007,9 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   a.chunk_state = (L.hot && v == 16 && a.lanes == shape.lanes)
                       ? reinterpret_cast<unsigned char*>(work + L.state_off)
                       : nullptr;
+  // introspection must not read stale counters when the path is skipped
+  if (L.hot && a.chunk_state == nullptr)
+    cudaMemsetAsync(a.hot_ctr, 0, 2 * sizeof(int), stream);
   const int col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
   const bool weighted = transpose_weights != nullptr;
 
