@@ -28,6 +28,7 @@
 //     embedding_lookup_ops.cuh:610-618, overflows at rows*width >= 2^31).
 //
 // L2/HBM-bound gather + stream-out: no tensor cores.
+#include <algorithm>
 #include <atomic>
 
 #include "common.cuh"
@@ -45,6 +46,7 @@ struct BwdArgs {
   void* inverse_mapping;
   float* scratch;       // [num_chunks][2][width]: head partial, tail partial
   float* group_part;    // [num_chunks / kFixGroup][width]: sums of through groups
+  int* tail_list;       // [1 + num_chunks]: count, then the chunks with a tail
   int* meta;            // [num_chunks][2] : head kind, has tail
   long long* meta_row;  // [num_chunks][2] : head row, tail row
   int64_t row_bytes;
@@ -491,6 +493,8 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
     a.meta[chunk * 2 + 1] = has_tail;
     a.meta_row[chunk * 2 + 0] = static_cast<long long>(head_row);
     a.meta_row[chunk * 2 + 1] = static_cast<long long>(tail_row);
+    // work list of the fix-up (any order: every chain is summed on its own)
+    if (has_tail) a.tail_list[1 + atomicAdd(a.tail_list, 1)] = chunk;
   }
 }
 
@@ -534,11 +538,13 @@ __global__ void __launch_bounds__(kCtaThreads)
 
 // Fix-up, level 2: adds, in chunk order, the partials of every run that crosses
 // chunk edges: tail of the chunk where the run starts + heads of the following
-// chunks, whole "through" groups taken from level 1.  One small CTA (64
-// threads) per chunk: most chunks have nothing to do or a two-element chain, so
-// what matters is how many of them an SM holds (32 CTAs) while each waits for
-// its three or four dependent round trips; 256-thread CTAs took 30 us at C2,
-// one warp per chunk 38 us.  A thread owns every 64th column, four columns and
+// chunks, whole "through" groups taken from level 1.  Small CTAs (64 threads,
+// 32 per SM) walk the list of chunks with a tail that the main kernel wrote:
+// most chains have two elements, so what matters is how many of them an SM
+// holds while each waits for its three or four dependent round trips, and not
+// launching a CTA for every chunk that has nothing to do (one 256-thread CTA
+// per chunk took 30 us at C2, one 64-thread CTA per chunk 24 us, one warp per
+// chunk 38 us).  A thread owns every 64th column, four columns and
 // eight chain elements in flight.  Every sum has a fixed association.
 constexpr int kFixThreads = 64;
 
@@ -546,9 +552,10 @@ template <typename T>
 __global__ void __launch_bounds__(kFixThreads)
     BwdFixupKernel(const BwdArgs a) {
   __shared__ int s_len;
-  const int c0 = blockIdx.x;
-  if (a.meta[c0 * 2 + 1] == 0) return;
   const int tid = threadIdx.x;
+  const int n_tails = a.tail_list[0];
+  for (int li = blockIdx.x; li < n_tails; li += gridDim.x) {
+  const int c0 = a.tail_list[1 + li];
   // chain = chunks c0+1 .. c0+len; the last one has kind "ends".
   if (tid == 0) s_len = 0x7fffffff;
   __syncthreads();
@@ -649,6 +656,8 @@ __global__ void __launch_bounds__(kFixThreads)
       StoreOneAs<T>(dst, val);
     }
   }
+  __syncthreads();  // s_len is reused for the next chain of this CTA
+  }  // chains of this CTA
 }
 
 namespace {
@@ -664,7 +673,7 @@ struct BwdLayout {
   int cta_nz;
   int num_ctas;
   int num_chunks;
-  size_t scratch_off, group_off, meta_off, row_off, total;
+  size_t scratch_off, group_off, meta_off, row_off, tail_off, total;
   // hot-row path
   bool hot;
   int hot_min_chunks, hot_cap;
@@ -727,6 +736,8 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(int), 256);
   L.row_off = off;
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(long long), 256);
+  L.tail_off = off;
+  off += AlignUp(static_cast<size_t>(L.num_chunks + 1) * sizeof(int), 256);
   const int hot_env = BackwardHotPathEnabled();
   static const int hot_nnz = EnvInt("CUEMBED_BWD_HOT_NNZ", 2048);
   const int chunk_nz = lanes * rounds;
@@ -803,7 +814,9 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   const int groups = a.num_chunks / kFixGroup;
   if (groups > 0)
     BwdGroupKernel<<<dim3(groups, wtiles), kCtaThreads, 0, stream>>>(a);
-  BwdFixupKernel<T><<<a.num_chunks, kFixThreads, 0, stream>>>(a);
+  // persistent over the list of chunks with a tail (written by the main kernel)
+  const int fix_ctas = std::min(a.num_chunks, a.sm_slots * 32);
+  BwdFixupKernel<T><<<fix_ctas, kFixThreads, 0, stream>>>(a);
   CountLaunch(groups > 0 ? 3 : 2);
 }
 
@@ -981,6 +994,9 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   a.group_part = reinterpret_cast<float*>(work + L.group_off);
   a.meta = reinterpret_cast<int*>(work + L.meta_off);
   a.meta_row = reinterpret_cast<long long*>(work + L.row_off);
+  a.tail_list = reinterpret_cast<int*>(work + L.tail_off);
+  if (cudaMemsetAsync(a.tail_list, 0, sizeof(int), stream) != cudaSuccess)
+    return CUEMBED_ERR_CUDA;
   a.row_bytes = row_bytes;
   a.width = embed_width;
   a.nnz = nnz;
