@@ -163,3 +163,86 @@ def test_backward_full_size_exact_and_idempotent(c2):
         n1 = min(nnz, n0 + (1 << 19))
         want_t.index_add_(0, ti[n0:n1].long(), grad_y[ts[n0:n1].long()].float())
     assert torch.equal(table, -(2.0 ** -6) * want_t)
+
+
+# ---------------------------------------------------------------- C3 shapes
+def test_c3_csr_weighted_int64_full_size_exact():
+    """BASELINE.json configs[2]: CSR bags of U{0..64} lookups (mean 32), weighted
+    sum and mean, width 128, fp32 and bf16, int64 indices, batch 131072 -- on an
+    integer-valued table with the reference's {0.5, 0.25} weights every product
+    and partial sum is exact, so forward, transpose (weights travel with their
+    pairs) and backward must equal torch's segment sums bit for bit."""
+    rows, width, batch, hot = 10_000_000, 128, 131072, 64
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~40 GB of device memory")
+    wl = datagen.make_workload(rows, width, batch, hot, alpha=ALPHA, csr=True, weighted=True,
+                               index_dtype=np.int64, offset_dtype=np.int32, seed=77)
+    nnz = wl.nnz
+    indices = torch.from_numpy(wl.indices).to(DEV)
+    offsets = torch.from_numpy(wl.offsets).to(DEV)
+    weights32 = torch.from_numpy(wl.weights).to(DEV)
+    g = torch.Generator(device=DEV)
+    g.manual_seed(7)
+    lens = (offsets[1:] - offsets[:-1]).long()
+    bag_of = torch.repeat_interleave(torch.arange(batch, device=DEV), lens)
+    for dt in (torch.float32, torch.bfloat16):
+        table = torch.empty(rows, width, dtype=dt, device=DEV)
+        for r0 in range(0, rows, 1 << 21):
+            r1 = min(rows, r0 + (1 << 21))
+            table[r0:r1] = torch.randint(-4, 5, (r1 - r0, width), generator=g, device=DEV).to(dt)
+        w = weights32.to(dt)
+        # forward, weighted sum
+        out = torch.full((batch, width), float("nan"), dtype=dt, device=DEV)
+        ce.EmbeddingForward(table, width, indices, offsets, w, batch, 0, ce.CombineMode.kSum, out)
+        torch.cuda.synchronize()
+        want = torch.zeros(batch, width, dtype=torch.float32, device=DEV)
+        for n0 in range(0, nnz, 1 << 19):
+            n1 = min(nnz, n0 + (1 << 19))
+            want.index_add_(0, bag_of[n0:n1],
+                            table[indices[n0:n1]].float() * weights32[n0:n1, None])
+        assert float(want.abs().max()) <= 128  # exact in bf16 too (multiples of 1/4)
+        assert torch.equal(out.float(), want)
+        # unweighted mean: sum * (1 / len), zero vector for empty bags
+        ce.EmbeddingForward(table, width, indices, offsets, None, batch, 0,
+                            ce.CombineMode.kMean, out)
+        torch.cuda.synchronize()
+        plain = torch.zeros(batch, width, dtype=torch.float32, device=DEV)
+        for n0 in range(0, nnz, 1 << 19):
+            n1 = min(nnz, n0 + (1 << 19))
+            plain.index_add_(0, bag_of[n0:n1], table[indices[n0:n1]].float())
+        inv_len = torch.where(lens > 0, 1.0 / lens.float(), torch.zeros_like(lens, dtype=torch.float32))
+        assert torch.equal(out.float(), (plain * inv_len[:, None]).to(dt).float())
+        # transpose with weights + backward (weighted, compressed)
+        row_ids = torch.empty(nnz, dtype=torch.int64, device=DEV)
+        ce.ExtractRowIdsFromCSR(offsets, batch, row_ids)
+        assert torch.equal(row_ids, bag_of)
+        t_idx, t_sid, t_w = (torch.empty_like(indices), torch.empty_like(indices),
+                             torch.empty_like(w))
+        remapped = torch.empty_like(indices)
+        lwork = max(ce.Transpose(row_ids, indices, w, nnz, None, None, None, None),
+                    ce.ComputeCompressedGradIndices(indices, nnz, None, None))
+        work = torch.empty(lwork, dtype=torch.uint8, device=DEV)
+        ce.Transpose(row_ids, indices, w, nnz, t_idx, t_sid, t_w, work)
+        ce.ComputeCompressedGradIndices(t_idx, nnz, remapped, work)
+        torch.cuda.synchronize()
+        order = torch.sort(indices * batch + row_ids).indices
+        assert torch.equal(t_idx, indices[order]) and torch.equal(t_sid, row_ids[order])
+        assert torch.equal(t_w.float(), weights32[order])
+        num_unique = int(remapped[-1].item()) + 1
+        grad_y = torch.randint(-10, 11, (batch, width), generator=g, device=DEV).to(dt)
+        grad = torch.full((num_unique, width), float("nan"), dtype=dt, device=DEV)
+        inv = torch.empty(num_unique, dtype=torch.int64, device=DEV)
+        ce.EmbeddingBackward(grad_y, width, num_unique, nnz, t_idx, t_sid, remapped, t_w,
+                             True, grad, inv)
+        torch.cuda.synchronize()
+        want_g = torch.zeros(num_unique, width, dtype=torch.float32, device=DEV)
+        for n0 in range(0, nnz, 1 << 19):
+            n1 = min(nnz, n0 + (1 << 19))
+            want_g.index_add_(0, remapped[n0:n1],
+                              grad_y[t_sid[n0:n1]].float() * t_w[n0:n1, None].float())
+        assert float(want_g.abs().max()) < 2 ** 22  # multiples of 1/4 below 2^24 / 4
+        assert torch.equal(grad.float(), want_g.to(dt).float())
+        assert torch.equal(inv, torch.unique_consecutive(t_idx))
+        del table, out, want, plain, grad, want_g
+        torch.cuda.empty_cache()
