@@ -605,7 +605,11 @@ SortLayout MakeSortLayout(int nnz, int idx_type, int wbytes) {
   SortLayout L;
   const int nd = static_cast<int>(IndexSize(idx_type));
   static const int items_env = EnvInt("CUEMBED_SORT_ITEMS", 0);
-  L.items = items_env > 0 ? items_env : 8;
+  // 16 keys per thread (4096-key tiles) once there are enough tiles to keep the
+  // SMs busy: fewer per-tile fixed costs (counter reset, digit scan, look-back);
+  // measured at C2 under graph replay: transpose 0.177 -> 0.170 ms.  Smaller
+  // problems keep 2048-key tiles for parallelism.
+  L.items = items_env > 0 ? items_env : (nnz >= (2 << 20) ? 16 : 8);
   if (L.items != 8 && L.items != 16) L.items = 8;
   L.tile = L.items * kCtaThreads;
   L.num_tiles = nnz > 0 ? (nnz + L.tile - 1) / L.tile : 0;
