@@ -71,12 +71,27 @@ def make_arm(lib, prefix):
                                           P(st["rem"]), None, 1, P(st["grad"]), P(st["inv"]), stream())
     return st, [("forward", fwd), ("transpose", tr), ("backward", bwd)]
 
-def time_arm(stages):
+def time_arm(stages, graph=False):
+    """graph=True: every stage captured once into a CUDA graph and replayed,
+    for both arms alike (bench.py's default launch mode)."""
     res = {}
     for name, fn in stages:
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        if graph:
+            try:
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    fn()
+                fn = g_.replay
+                fn()
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                res[name] = float("nan")
+                print(f"graph capture failed for {name}: {type(e).__name__}: {e}", file=sys.stderr)
+                torch.cuda.synchronize()
+                continue
         tot = 0.0
         for _ in range(steps):
             flush.fill_(1)
@@ -96,6 +111,8 @@ st_o, stages_o = make_arm(ours, "cuembed_")
 st_r, stages_r = make_arm(ref, "refgpu_")
 t_o = time_arm(stages_o)
 t_r = time_arm(stages_r)
+tg_o = time_arm(stages_o, graph=True)
+tg_r = time_arm(stages_r, graph=True)
 # cross-check (the reference GPU backward accumulates in fp16 with atomics:
 # compare in value with a tolerance; the backward buffers are re-zeroed first)
 st_o["grad"].zero_(); st_r["grad"].zero_()
@@ -114,5 +131,9 @@ out = {"workload": workload, "steps": steps, "nnz": nnz,
        "reference_gpu_ms": {k: round(v, 4) for k, v in t_r.items()},
        "speedup": {k: round(t_r[k] / t_o[k], 3) for k in t_o},
        "total_ms": {"ours": round(sum(t_o.values()), 4), "reference_gpu": round(sum(t_r.values()), 4)},
+       "graph_replay": {"ours_ms": {k: round(v, 4) for k, v in tg_o.items()},
+                        "reference_gpu_ms": {k: round(v, 4) for k, v in tg_r.items()},
+                        "total_ms": {"ours": round(sum(tg_o.values()), 4),
+                                     "reference_gpu": round(sum(tg_r.values()), 4)}},
        "cross_check": chk}
 print(json.dumps(out))
