@@ -1,4 +1,5 @@
 """bench.py --gpus N (N > 1): the row-sharded path, one process per GPU.
+(Bench harness: lives next to the other benchmark drivers, not in the package.)
 
 Weak scaling of the headline workload: every rank owns a C2-sized shard
 (10 M x 256 fp16 rows), the global table has N x 10 M rows, the global batch
@@ -62,7 +63,7 @@ def run(args, rank, local_rank, world):
     if transport == "p2p":
         ok = torch.tensor([1], device=torch.device("cuda", local_rank))
         try:
-            from . import peer
+            from cuembed_b200 import peer
             probe = peer.PeerBuffer(4096)
             probe.close()
         except Exception as e:  # noqa: BLE001 -- any failure means "cannot map"
@@ -105,6 +106,59 @@ def make_inputs(args, rank, world, dev):
     return cfg, tdt, idt, rows, batch, nnz, per, indices, table, grad_slice
 
 
+def verify_p2p(emb, ce, table, indices, grad_slice, batch, hot, world, rank, dev):
+    """Real-rank numerics check, run AFTER the timed region: the sharded
+    forward / backward against an independent computation made of plain torch
+    ops + NCCL collectives.  The table is replaced in place by round(8 * table)
+    (integers in [-8, 8]) and grad_y is the integer recipe, so every partial and
+    every sum is exact in fp32 AND in 16-bit partials: the comparison is
+    bit-exact whatever the summation order or the wire type.
+      forward : the first 512 bags of every rank's slice; each rank adds the
+                rows it owns, NCCL all_reduce sums the ranks
+      backward: the whole compressed gradient of this rank's shard against
+                index_add over an NCCL all_gather of grad_y, and the row list"""
+    w = table.shape[1]
+    lo, hi = emb.lo, emb.hi
+    per = batch // world
+    nnz = batch * hot
+    table.mul_(8).round_()
+    out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+    nb = min(per, 512)
+    sample = torch.cat([torch.arange(r * per, r * per + nb, device=dev) for r in range(world)])
+    idx = indices.view(batch, hot)[sample].long()
+    own = (idx >= lo) & (idx < hi)
+    local = (idx - lo).clamp_(0, max(hi - lo - 1, 0))
+    want = torch.zeros(world * nb, w, dtype=torch.float32, device=dev)
+    for j in range(hot):  # one lookup column at a time keeps the temporaries small
+        want += table[local[:, j]].float() * own[:, j, None]
+    dist.all_reduce(want)
+    ok_f = bool(torch.equal(out[:nb].float(), want[rank * nb:(rank + 1) * nb]))
+    grad, rows_out = emb.backward(grad_slice, ctx, True)
+    full_gy = torch.empty(batch, w, dtype=grad_slice.dtype, device=dev)
+    dist.all_gather_into_tensor(full_gy, grad_slice.contiguous())
+    flat = indices.long()
+    mine = (flat >= lo) & (flat < hi)
+    li = flat[mine]
+    lb = (torch.arange(nnz, device=dev) // hot)[mine]
+    uniq, inverse = torch.unique(li, return_inverse=True)
+    want_g = torch.zeros(uniq.numel(), w, dtype=torch.float32, device=dev)
+    for n0 in range(0, li.numel(), 1 << 19):
+        n1 = min(li.numel(), n0 + (1 << 19))
+        want_g.index_add_(0, inverse[n0:n1], full_gy[lb[n0:n1]].float())
+    ok_b = (grad.shape[0] == uniq.numel()
+            and bool(torch.equal(grad, want_g.to(grad.dtype)))
+            and bool(torch.equal(rows_out.long(), uniq)))
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(ok_f), int(ok_b), int(emb.status() == 0)], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    f, b, st = (bool(x) for x in ok.tolist())
+    return {"verified": f and b and st, "forward": f, "backward": b, "no_wait_timeout": st,
+            "how": "after the timed region, every rank: integer-valued table (round(8 * table)) "
+                   "and integer grad_y -> exact sums; forward of 512 bags per rank slice vs "
+                   "torch gather + NCCL all_reduce, whole compressed shard gradient + row list vs "
+                   "index_add over an NCCL all_gather; bit-exact; AND over ranks"}
+
+
 def run_p2p(args, rank, local_rank, world):
     """One step = forward (pool + push over NVLink, signal, rank-ordered reduce)
     -> [copy engines push grad_y slices || select + sort of the own lookups]
@@ -120,7 +174,7 @@ def run_p2p(args, rank, local_rank, world):
         make_inputs(args, rank, world, dev)
     w, hot = cfg["embed_width"], cfg["hotness"]
     shard_rows = cfg["num_categories"]
-    pdt = {"f32": torch.float32, "table": tdt}[getattr(args, "partial_dtype", "f32")]
+    pdt = {"f32": torch.float32, "table": tdt}[getattr(args, "partial_dtype", "table")]
     emb = PeerShardedEmbedding(table, rows, partial_dtype=pdt)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -135,6 +189,7 @@ def run_p2p(args, rank, local_rank, world):
     g2, _ = emb.backward(grad_slice, ctx)
     torch.cuda.synchronize()
     state = {}
+    known_sizes = bool(getattr(args, "known_sizes", False))
 
     def one_step(rec=None):
         flush.fill_(1)
@@ -143,9 +198,17 @@ def run_p2p(args, rank, local_rank, world):
         ev[0].record(stream)
         out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
         ev[1].record(stream)
-        pend = emb.backward_begin(grad_slice, ctx, True, local_nnz=local_nnz)
-        ev[2].record(stream)
-        emb.backward_finish(pend, grad=grad, inverse=inv)
+        if known_sizes:
+            pend = emb.backward_begin(grad_slice, ctx, True, local_nnz=local_nnz)
+            ev[2].record(stream)
+            emb.backward_finish(pend, grad=grad, inverse=inv)
+        else:
+            # a loop whose indices change every step: the host reads the number
+            # of owned lookups (after the select) and the number of unique rows
+            # (after the sort) back in EVERY step to size the sort / gradient
+            pend = emb.backward_begin(grad_slice, ctx, True)
+            ev[2].record(stream)
+            emb.backward_finish(pend)
         ev[3].record(stream)
         state["out"] = out
         if rec is not None:
@@ -230,6 +293,7 @@ def run_p2p(args, rank, local_rank, world):
         d2h = world * (per * w * es + num_unique * (w * es + indices.element_size()))
 
     clocks = sampler.stop() if rank == 0 else None
+    verified = verify_p2p(emb, ce, table, indices, grad_slice, batch, hot, world, rank, dev)
     peak, peak_src = bench.measured_peaks()
     es = table.element_size()
     isz = indices.element_size()
@@ -247,6 +311,7 @@ def run_p2p(args, rank, local_rank, world):
             "value": round(nnz / (ms_per_step * 1e-3), 1), "unit": "lookups/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "verified": verified["verified"], "verification": verified,
             "scaling": "strong" if cfg.get("global_problem") else "weak",
             "vs_baseline": None, "dtype": cfg["dtype"],
             "data": "synthetic",
@@ -260,6 +325,10 @@ def run_p2p(args, rank, local_rank, world):
                                       f"slices pushed by copy engines during the local sort",
                        "transport": "p2p",
                        "l2": "flushed before every step (512 MB write)",
+                       "sizes": ("local nnz / num_unique known from an earlier identical step "
+                                 "(--known-sizes): no host read-back" if known_sizes else
+                                 "local nnz and num_unique read back by the host in every step "
+                                 "(2 stream syncs per step, inside the timed region)"),
                        "nnz_global": nnz, "nnz_local_rank0": local_nnz,
                        "num_unique_rank0": num_unique,
                        "nvlink_bytes_out_per_rank": {"forward": nvlink_fwd, "backward": nvlink_bwd},

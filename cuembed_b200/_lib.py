@@ -61,11 +61,13 @@ SIGNATURES = {
                                         ctypes.c_longlong, ctypes.c_longlong,
                                         ctypes.POINTER(_vp), _ci, _ci, _vp]),
     "cuembed_shard_signal": (_ci, [ctypes.POINTER(_vp), _ci, _ci, _ci, ctypes.c_uint, _vp]),
-    "cuembed_shard_wait": (_ci, [_vp, _ci, _ci, ctypes.c_uint, _vp]),
+    "cuembed_shard_wait": (_ci, [_vp, _ci, _ci, ctypes.c_uint, _vp, _sz, _vp]),
+    "cuembed_shard_set_timeout_ms": (_ci, [ctypes.c_longlong]),
     "cuembed_shard_reduce_finalize": (_ci, [_vp, _ci, _ci, _vp, _ci, ctypes.c_uint, _ci,
                                             _ci, _ci, _vp, _ci, _ci, _ci, _vp, _ci, _vp,
                                             _ci, _vp]),
     "cuembed_shard_allgather_push": (_ci, [_vp, _sz, ctypes.POINTER(_vp), _ci, _ci, _vp]),
+    "cuembed_microbench_gather": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }
 

@@ -179,25 +179,35 @@ int cuembed_backward(const void* grad_y, int dtype, int embed_width,
   if (rc != CUEMBED_OK) return rc;
   if (nnz == 0 && skip_grad_init) return CUEMBED_OK;
 
-  static cudaMemPool_t pools[64] = {nullptr};
+  // one pool per device, created once under a lock (two host threads may make
+  // their first call on the same device at the same time)
+  static cudaMemPool_t pools[kMaxDevices] = {nullptr};
+  static std::mutex pools_mu;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
     return CUEMBED_ERR_CUDA;
-  if (pools[dev] == nullptr) {
-    cudaMemPoolProps props;
-    std::memset(&props, 0, sizeof(props));
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    cudaMemPool_t pool;
-    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) return CUEMBED_ERR_CUDA;
-    unsigned long long threshold = ~0ull;  // never trim: reuse across calls
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    pools[dev] = pool;
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(pools_mu);
+    if (pools[dev] == nullptr) {
+      cudaMemPoolProps props;
+      std::memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      cudaMemPool_t created;
+      if (cudaMemPoolCreate(&created, &props) != cudaSuccess)
+        return CUEMBED_ERR_CUDA;
+      unsigned long long threshold = ~0ull;  // never trim: reuse across calls
+      cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold,
+                              &threshold);
+      pools[dev] = created;
+    }
+    pool = pools[dev];
   }
   void* work = nullptr;
-  if (cudaMallocFromPoolAsync(&work, lwork, pools[dev], stream) != cudaSuccess)
+  if (cudaMallocFromPoolAsync(&work, lwork, pool, stream) != cudaSuccess)
     return CUEMBED_ERR_CUDA;
   rc = LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows, nnz,
                       idx_type, transpose_indices, transpose_sample_ids,

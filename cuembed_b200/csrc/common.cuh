@@ -11,6 +11,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/cuembed_b200.h"
 
 namespace cuembed_b200 {
@@ -25,32 +28,57 @@ struct DeviceInfo {
   int max_smem_optin;
 };
 
-// Cached per-device properties (benign race: every thread writes the same
-// values).
-inline const DeviceInfo& GetDeviceInfo() {
-  static DeviceInfo info[64];
-  static bool ready[64] = {false};
+constexpr int kMaxDevices = 64;
+
+inline int CurrentDeviceSlot() {
   int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!ready[dev]) {
-    DeviceInfo d;
-    d.sm_count = 0;
-    d.max_smem_optin = 0;
-    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&d.max_smem_optin,
-                           cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    // Workspace queries must also work where no device is visible (build
-    // hosts): size them for the part this library is written for.
-    if (d.sm_count <= 0) {
-      d.sm_count = 148;
-      cudaGetLastError();
+  if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
+
+// Cached per-device properties.  Each slot is published with release /
+// acquire ordering, so a thread that sees `ready` also sees the values.
+inline const DeviceInfo& GetDeviceInfo() {
+  static DeviceInfo info[kMaxDevices];
+  static std::atomic<bool> ready[kMaxDevices];
+  static std::mutex mu;
+  const int dev = CurrentDeviceSlot();
+  if (!ready[dev].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ready[dev].load(std::memory_order_relaxed)) {
+      DeviceInfo d;
+      d.sm_count = 0;
+      d.max_smem_optin = 0;
+      cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&d.max_smem_optin,
+                             cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      // Workspace queries must also work where no device is visible (build
+      // hosts): size them for the part this library is written for.
+      if (d.sm_count <= 0) {
+        d.sm_count = 148;
+        cudaGetLastError();
+      }
+      info[dev] = d;
+      ready[dev].store(true, std::memory_order_release);
     }
-    info[dev] = d;
-    ready[dev] = true;
   }
   return info[dev];
 }
+
+// One int per device for values that are device / context properties (kernel
+// occupancy, "function attribute already raised"): a process that drives
+// several GPUs must not reuse what it learned on the first one.  0 = unset.
+// Racing first calls on one device compute the same value (idempotent).
+struct PerDeviceInt {
+  std::atomic<int> v[kMaxDevices];
+  PerDeviceInt() {
+    for (auto& x : v) x.store(0, std::memory_order_relaxed);
+  }
+  int Get() const {
+    return v[CurrentDeviceSlot()].load(std::memory_order_acquire);
+  }
+  void Set(int x) { v[CurrentDeviceSlot()].store(x, std::memory_order_release); }
+};
 
 // Environment-variable tuning knob (read once per name per process by callers
 // that cache the result).

@@ -34,15 +34,18 @@ int Log2(int v) {
 }
 
 // Persistent grid: SM count x resident CTAs of this kernel, capped by the
-// amount of work.  `occ_cache` is a per-instantiation static of the caller.
-int PersistentGrid(const void* kernel, int* occ_cache, int64_t work_ctas) {
-  if (*occ_cache == 0) {
+// amount of work.  `occ_cache` is a per-instantiation, per-device static of the
+// caller.
+int PersistentGrid(const void* kernel, PerDeviceInt* occ_cache,
+                   int64_t work_ctas) {
+  int occ = occ_cache->Get();
+  if (occ == 0) {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kCtaThreads, 0);
-    *occ_cache = n > 0 ? n : 1;
+    occ = n > 0 ? n : 1;
+    occ_cache->Set(occ);
   }
-  const int64_t cap =
-      static_cast<int64_t>(GetDeviceInfo().sm_count) * (*occ_cache);
+  const int64_t cap = static_cast<int64_t>(GetDeviceInfo().sm_count) * occ;
   int64_t g = work_ctas < cap ? work_ctas : cap;
   return static_cast<int>(g < 1 ? 1 : g);
 }
@@ -52,7 +55,7 @@ void LaunchPool(const FwdArgs& a, cudaStream_t stream) {
   static const int unroll = EnvInt("CUEMBED_FWD_UNROLL", 8);
   const int groups_per_cta = kCtaThreads / a.lanes;
   const int64_t work_ctas = (a.batch + groups_per_cta - 1) / groups_per_cta;
-  static int occ4 = 0, occ8 = 0, occ16 = 0;
+  static PerDeviceInt occ4, occ8, occ16;
   if (unroll == 4) {
     auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 4>;
     const int grid =
@@ -121,11 +124,27 @@ void LaunchConcat(const ConcatArgs& a, cudaStream_t stream) {
   const int64_t work_ctas =
       (a.nnz + static_cast<int64_t>(groups_per_cta) * 4 - 1) /
       (static_cast<int64_t>(groups_per_cta) * 4);
-  static int occ = 0;
+  static PerDeviceInt occ;
   const int grid =
       PersistentGrid(reinterpret_cast<const void*>(k), &occ, work_ctas);
   k<<<grid, kCtaThreads, 0, stream>>>(a);
   CountLaunch();
+}
+
+// Vector width (bytes of INPUT per lane and step) for the pooled kernels:
+// starts at `v0` and halves until the OR of the input addresses / pitches is a
+// multiple of v and the OR of the output addresses / pitches is a multiple of
+// the matching output store (v * sizeof(out) / sizeof(in), at most 16 bytes).
+// Returns 0 if not even 4-byte input vectors are possible.
+int PickPoolVector(int v0, uint64_t in_bits, uint64_t out_bits, int in_dtype,
+                   int out_dtype) {
+  for (int v = v0; v >= 4; v /= 2) {
+    const int64_t out_vec =
+        static_cast<int64_t>(v) * ElemSize(out_dtype) / ElemSize(in_dtype);
+    if (in_bits % v == 0 && out_bits % (out_vec > 16 ? 16 : out_vec) == 0)
+      return v;
+  }
+  return 0;
 }
 
 // Largest power-of-two <= 16 that divides every value in `bits` (an OR of
@@ -142,7 +161,7 @@ void LaunchPoolMulti(const FwdMultiArgs& m, int num_tables, int col_tiles,
                      cudaStream_t stream) {
   const int groups_per_cta = kCtaThreads / lanes;
   const int64_t work_ctas = (max_batch + groups_per_cta - 1) / groups_per_cta;
-  static int occ_w = 0, occ_u = 0;
+  static PerDeviceInt occ_w, occ_u;
   int grid;
   if (weighted) {
     auto k = FwdPoolMultiKernel<T, V, IdxT, true>;
@@ -227,16 +246,9 @@ int LaunchForwardMulti(int num_tables, const void* const* params, int in_dtype,
     out_bits |= reinterpret_cast<uint64_t>(rets[t]);
   }
   if (!any) return CUEMBED_OK;
-  int v = shape.vec_bytes;
-  for (;;) {
-    const int64_t out_vec =
-        static_cast<int64_t>(v) * ElemSize(out_dtype) / ElemSize(in_dtype);
-    const bool ok = (in_bits % v == 0) &&
-                    (out_bits % (out_vec > 16 ? 16 : out_vec) == 0);
-    if (ok || v == 4) break;
-    v /= 2;
-  }
-  if (v < 4 || in_bits % v != 0) return CUEMBED_ERR_ARGUMENT;
+  const int v =
+      PickPoolVector(shape.vec_bytes, in_bits, out_bits, in_dtype, out_dtype);
+  if (v == 0) return CUEMBED_ERR_ARGUMENT;
 
   const int nvec = static_cast<int>(row_bytes / v);
   const int lanes = Pow2Ceil(nvec) < 32 ? Pow2Ceil(nvec) : 32;
@@ -352,21 +364,16 @@ int LaunchForward(const void* params, int in_dtype, int embed_width,
   // vector holds the same NE elements of the output type.
   const int64_t out_row_bytes =
       static_cast<int64_t>(embed_width) * ElemSize(out_dtype);
-  int v = shape.vec_bytes;
-  for (;;) {
-    const uint64_t in_bits =
-        reinterpret_cast<uint64_t>(params) | static_cast<uint64_t>(row_bytes);
-    const int64_t out_vec =
-        static_cast<int64_t>(v) * ElemSize(out_dtype) / ElemSize(in_dtype);
-    const uint64_t out_bits = reinterpret_cast<uint64_t>(ret) |
-                              static_cast<uint64_t>(out_row_bytes);
-    const bool ok = (in_bits % v == 0) &&
-                    (out_bits % (out_vec > 16 ? 16 : out_vec) == 0);
-    if (ok || v == 4) break;
-    v /= 2;
-  }
-  if (v < static_cast<int>(ElemSize(in_dtype)) * 1 || v < 4)
-    return CUEMBED_ERR_ARGUMENT;
+  // Widest vector that both the input side (table pointer, row pitch) and
+  // the output side (ret pointer, output pitch, NE output elements per store)
+  // allow; a pointer that does not even allow 4-byte input vectors / the
+  // matching output store is an argument error, not a misaligned access.
+  const int v = PickPoolVector(
+      shape.vec_bytes,
+      reinterpret_cast<uint64_t>(params) | static_cast<uint64_t>(row_bytes),
+      reinterpret_cast<uint64_t>(ret) | static_cast<uint64_t>(out_row_bytes),
+      in_dtype, out_dtype);
+  if (v == 0) return CUEMBED_ERR_ARGUMENT;
 
   FwdArgs a;
   a.params = params;

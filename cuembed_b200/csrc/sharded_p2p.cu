@@ -34,6 +34,7 @@
 // cannot get there before having seen that peer's next signal.
 // A wait that sees no signal for kWaitTimeoutNs gives up and raises the status
 // word instead of hanging the device.
+#include <atomic>
 #include <cstring>
 
 #include "common.cuh"
@@ -43,7 +44,22 @@
 namespace cuembed_b200 {
 
 constexpr int kMaxWorld = CUEMBED_MAX_WORLD;
-constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;
+// How long a wait spins before it gives up (a stalled peer: first-iteration
+// compile, data-loader hiccup, checkpoint).  Default 60 s; CUEMBED_PEER_TIMEOUT_MS
+// or cuembed_shard_set_timeout_ms() change it.  A wait that gives up raises the
+// status word AND poisons what depends on it (NaN output / NaN gather slice),
+// so stale peer data can never pass for a result.
+std::atomic<long long> g_wait_timeout_ms{-1};
+
+unsigned long long WaitTimeoutNs() {
+  long long ms = g_wait_timeout_ms.load();
+  if (ms < 0) {
+    ms = EnvInt("CUEMBED_PEER_TIMEOUT_MS", 60000);
+    if (ms <= 0) ms = 60000;
+    g_wait_timeout_ms.store(ms);
+  }
+  return static_cast<unsigned long long>(ms) * 1000000ull;
+}
 
 struct PeerPtrs {
   void* p[kMaxWorld];
@@ -70,20 +86,29 @@ __device__ __forceinline__ unsigned long long GlobalTimerNs() {
 }
 
 // The first `world` threads of the CTA each wait for one rank's flag to reach
-// `epoch` (wrap-around safe), then the CTA proceeds.
-__device__ __forceinline__ void WaitForPeers(const unsigned* flags, int world,
-                                             unsigned epoch, unsigned* status) {
+// `epoch` (wrap-around safe), then the CTA proceeds.  Returns a bit mask of
+// the ranks whose signal did not arrive within `timeout_ns` (0 = all arrived);
+// the status word keeps 1 + the last such rank until the host clears it.
+__device__ __forceinline__ unsigned WaitForPeers(const unsigned* flags,
+                                                 int world, unsigned epoch,
+                                                 unsigned* status,
+                                                 unsigned long long timeout_ns) {
+  __shared__ unsigned s_missing;
+  if (threadIdx.x == 0) s_missing = 0u;
+  __syncthreads();
   if (static_cast<int>(threadIdx.x) < world) {
     const unsigned long long t0 = GlobalTimerNs();
     while (static_cast<int>(LoadAcquireSys(flags + threadIdx.x) - epoch) < 0) {
-      if (GlobalTimerNs() - t0 > kWaitTimeoutNs) {
+      if (GlobalTimerNs() - t0 > timeout_ns) {
         atomicExch(status, 1u + threadIdx.x);
+        atomicOr(&s_missing, 1u << threadIdx.x);
         break;
       }
       __nanosleep(200);
     }
   }
   __syncthreads();
+  return s_missing;
 }
 
 __global__ void ShardSignalKernel(PeerPtrs flags, int world, int rank,
@@ -95,9 +120,21 @@ __global__ void ShardSignalKernel(PeerPtrs flags, int world, int rank,
   }
 }
 
+// Holds the stream until every rank has signalled `epoch`.  If a rank never
+// does, its slice of `poison` ([world] slices of poison_bytes, may be null) is
+// filled with 0xff bytes -- NaN in fp32 / fp16 / bf16 -- so that whatever is
+// computed from the incomplete gather buffer is visibly invalid.
 __global__ void ShardWaitKernel(const unsigned* flags, int world,
-                                unsigned epoch, unsigned* status) {
-  WaitForPeers(flags, world, epoch, status);
+                                unsigned epoch, unsigned* status,
+                                unsigned long long timeout_ns,
+                                unsigned char* poison, size_t poison_bytes) {
+  const unsigned missing = WaitForPeers(flags, world, epoch, status, timeout_ns);
+  if (missing == 0u || poison == nullptr) return;
+  for (int r = 0; r < world; ++r) {
+    if (((missing >> r) & 1u) == 0u) continue;
+    unsigned char* p = poison + static_cast<size_t>(r) * poison_bytes;
+    for (size_t i = threadIdx.x; i < poison_bytes; i += blockDim.x) p[i] = 0xff;
+  }
 }
 
 // ---------------------------------------------------------- pool and push
@@ -293,12 +330,15 @@ template <typename PT, typename WT, int VEC>
 __global__ void __launch_bounds__(kCtaThreads)
     ShardReduceFinalizeKernel(const PT* __restrict__ slots, int world,
                               const unsigned* flags, unsigned epoch,
-                              unsigned* status, int n_samples, int width,
+                              unsigned* status, unsigned long long timeout_ns,
+                              int n_samples, int width,
                               int mean, const void* offsets, int off64,
                               int num_hots, int sample0,
                               const WT* __restrict__ weights,
                               void* __restrict__ out, int out_dt) {
-  WaitForPeers(flags, world, epoch, status);
+  // a missing peer poisons the whole output (NaN), it is never summed stale
+  const bool poisoned =
+      WaitForPeers(flags, world, epoch, status, timeout_ns) != 0u;
   using PV = PartialVec<PT, VEC>;
   const int64_t total = static_cast<int64_t>(n_samples) * width;
   const int64_t nvec = total / VEC;
@@ -340,6 +380,10 @@ __global__ void __launch_bounds__(kCtaThreads)
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
         acc[k] = denom == 0.f ? 0.f : __fmul_rn(acc[k], scale);
+    }
+    if (poisoned) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = __int_as_float(0x7fc00000);
     }
     StoreFloatsAs<VEC>(out, i * VEC, out_dt, acc);
   }
@@ -422,14 +466,16 @@ int Log2i(int v) {
   return l;
 }
 
-int ResidentGrid(const void* kernel, int* occ_cache, int64_t work_ctas) {
-  if (*occ_cache == 0) {
+int ResidentGrid(const void* kernel, PerDeviceInt* occ_cache,
+                 int64_t work_ctas) {
+  int occ = occ_cache->Get();
+  if (occ == 0) {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kCtaThreads, 0);
-    *occ_cache = n > 0 ? n : 1;
+    occ = n > 0 ? n : 1;
+    occ_cache->Set(occ);
   }
-  const int64_t cap =
-      static_cast<int64_t>(GetDeviceInfo().sm_count) * (*occ_cache);
+  const int64_t cap = static_cast<int64_t>(GetDeviceInfo().sm_count) * occ;
   const int64_t g = work_ctas < cap ? work_ctas : cap;
   return static_cast<int>(g < 1 ? 1 : g);
 }
@@ -437,7 +483,7 @@ int ResidentGrid(const void* kernel, int* occ_cache, int64_t work_ctas) {
 template <typename T, int V, typename IdxT, bool WEIGHTED>
 void LaunchPush(const PushArgs& a, int col_tiles, cudaStream_t stream) {
   auto k = ShardPoolPushKernel<T, V, IdxT, WEIGHTED>;
-  static int occ = 0;
+  static PerDeviceInt occ;
   const int groups_per_cta = kCtaThreads / a.lanes;
   const int64_t work = (a.batch + groups_per_cta - 1) / groups_per_cta;
   const int grid = ResidentGrid(reinterpret_cast<const void*>(k), &occ, work);
@@ -485,8 +531,8 @@ void LaunchReduceVec(const void* slots, int world, const unsigned* flags,
   const int grid = static_cast<int>(ctas < cap ? (ctas < 1 ? 1 : ctas) : cap);
 #define REDUCE(VEC)                                                          \
   ShardReduceFinalizeKernel<PT, WT, VEC><<<grid, kCtaThreads, 0, stream>>>(  \
-      static_cast<const PT*>(slots), world, flags, epoch, status, n, width,  \
-      mean, offsets, off64, num_hots, sample0,                               \
+      static_cast<const PT*>(slots), world, flags, epoch, status,            \
+      WaitTimeoutNs(), n, width, mean, offsets, off64, num_hots, sample0,    \
       static_cast<const WT*>(weights), out, out_dt)
   if (vec == 4) {
     REDUCE(4);
@@ -627,20 +673,23 @@ int cuembed_shard_pool_push(const void* local_params, int in_dtype,
       static_cast<int64_t>(embed_width) * ElemSize(partial_dtype);
   RowShape shape;
   MakeRowShape(embed_width, in_dtype, &shape);
-  int v = shape.vec_bytes;
-  for (;;) {
-    uint64_t in_bits =
-        reinterpret_cast<uint64_t>(local_params) | static_cast<uint64_t>(row_bytes);
-    const int64_t out_vec =
-        static_cast<int64_t>(v) * ElemSize(partial_dtype) / ElemSize(in_dtype);
+  // widest vector every input AND every peer slot pointer allows (same rule
+  // as the single-GPU forward; a misaligned pointer is an argument error)
+  int v = 0;
+  {
+    const uint64_t in_bits = reinterpret_cast<uint64_t>(local_params) |
+                             static_cast<uint64_t>(row_bytes);
     uint64_t out_bits = static_cast<uint64_t>(out_row_bytes);
     for (int i = 0; i < world; ++i)
       out_bits |= reinterpret_cast<uint64_t>(slot_ptrs[i]);
-    const bool ok = (in_bits % v == 0) &&
-                    (out_bits % (out_vec > 16 ? 16 : out_vec) == 0);
-    if (ok || v == 4) break;
-    v /= 2;
+    for (int c = shape.vec_bytes; c >= 4 && v == 0; c /= 2) {
+      const int64_t out_vec =
+          static_cast<int64_t>(c) * ElemSize(partial_dtype) / ElemSize(in_dtype);
+      if (in_bits % c == 0 && out_bits % (out_vec > 16 ? 16 : out_vec) == 0)
+        v = c;
+    }
   }
+  if (v == 0) return CUEMBED_ERR_ARGUMENT;
   a.params = local_params;
   a.indices = indices;
   a.offsets = offsets;
@@ -714,7 +763,7 @@ int cuembed_shard_concat_push(const void* local_params, int dtype,
 #define CONCAT_PUSH(VV, IdxT)                                                \
   {                                                                          \
     auto k = ShardConcatPushKernel<VV, IdxT>;                                \
-    static int occ = 0;                                                      \
+    static PerDeviceInt occ;                                                 \
     const int grid = ResidentGrid(reinterpret_cast<const void*>(k), &occ,    \
                                   work);                                     \
     k<<<grid, kCtaThreads, 0, stream>>>(c);                                  \
@@ -747,8 +796,15 @@ int cuembed_shard_signal(void* const* flag_ptrs, int world, int rank,
   return CudaRc();
 }
 
+int cuembed_shard_set_timeout_ms(long long timeout_ms) {
+  if (timeout_ms <= 0) return CUEMBED_ERR_ARGUMENT;
+  g_wait_timeout_ms.store(timeout_ms);
+  return CUEMBED_OK;
+}
+
 int cuembed_shard_wait(const void* flags, int world, int channel,
-                       unsigned epoch, cuembed_stream_t stream_) {
+                       unsigned epoch, void* poison, size_t poison_bytes,
+                       cuembed_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (flags == nullptr || channel < 0 || channel >= CUEMBED_PEER_CHANNELS ||
       world < 1 || world > kMaxWorld)
@@ -756,8 +812,9 @@ int cuembed_shard_wait(const void* flags, int world, int channel,
   const unsigned* f = static_cast<const unsigned*>(flags);
   unsigned* status =
       const_cast<unsigned*>(f) + CUEMBED_PEER_CHANNELS * kMaxWorld;
-  ShardWaitKernel<<<1, 32, 0, stream>>>(f + channel * kMaxWorld, world, epoch,
-                                        status);
+  ShardWaitKernel<<<1, 256, 0, stream>>>(
+      f + channel * kMaxWorld, world, epoch, status, WaitTimeoutNs(),
+      static_cast<unsigned char*>(poison), poison_bytes);
   CountLaunch();
   return CudaRc();
 }

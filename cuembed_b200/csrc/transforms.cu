@@ -308,7 +308,6 @@ struct SortArgs {
   const int* plan;             // live mask, number of live passes
   uint32_t* lookback;          // [ND][num_tiles][256], zeroed
   int tile_pitch;              // unused
-  int debug;                   // tuning experiments only (CUEMBED_SORT_DEBUG)
   uint32_t* tile_counters;     // [ND], zeroed
   int nnz;
   int num_tiles;
@@ -502,7 +501,7 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
     // the pass (19 hops per tile on average, half of all warp samples,
     // profiles/r01_notes.md).
     uint32_t exclusive = 0;
-    if (tile > 0 && a.debug != 1) {
+    if (tile > 0) {
       constexpr int kLookWin = 8;
       int prev = tile - 1;
       bool done = false;
@@ -640,13 +639,16 @@ void LaunchPasses(const SortArgs& base, cudaStream_t stream) {
   constexpr int ND = sizeof(KeyT);
   const size_t smem = static_cast<size_t>(ITEMS) * kCtaThreads * 2 * sizeof(KeyT);
   auto kernel = RadixPassKernel<KeyT, WBYTES, ITEMS>;
-  static int ctas_per_sm = 0;
+  // function attributes and occupancy are per device: one cache slot per device
+  static PerDeviceInt ctas_per_sm_cache;
+  int ctas_per_sm = ctas_per_sm_cache.Get();
   if (ctas_per_sm == 0) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(smem));
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kCtaThreads, smem);
     ctas_per_sm = n > 0 ? n : 1;
+    ctas_per_sm_cache.Set(ctas_per_sm);
   }
   const int cap = GetDeviceInfo().sm_count * ctas_per_sm;
   const int grid = base.num_tiles < cap ? base.num_tiles : cap;
@@ -737,8 +739,6 @@ int LaunchTranspose(const void* rows, const void* cols, const void* weights,
   a.nnz = nnz;
   a.num_tiles = L.num_tiles;
   a.tile_pitch = L.tile_pitch;
-  static const int debug_env = EnvInt("CUEMBED_SORT_DEBUG", 0);
-  a.debug = debug_env;
   a.pass = 0;
   if (idx_type == CUEMBED_I64)
     LaunchSortTyped<int64_t>(a, hist, plan, wbytes, L.items, stream);

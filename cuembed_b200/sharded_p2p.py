@@ -53,14 +53,22 @@ class PeerShardedEmbedding:
     `buffers(kind, nbytes)` returns this rank's view of a symmetric allocation
     (peer.PeerBuffer by default; tests pass peer.LocalPeerGroup views together
     with explicit `rank` / `world` to run several virtual ranks in one process).
-    partial_dtype: torch.float32 (default: exact fp32 partial sums on the wire)
-    or the table's 16-bit dtype (half the NVLink bytes, one extra rounding per
-    partial sum).
+    partial_dtype: element type of the partial sums on the wire.  None (default)
+    = the table's own type: fp32 partials for fp32 tables (bit-exact), 16-bit
+    partials for fp16 / bf16 tables (half the NVLink bytes; every partial sum is
+    rounded once to the table type before the rank-ordered fp32 reduction, so
+    the result differs from the fp32-partial result by at most world roundings
+    of the 16-bit type -- the same order as the final rounding of the output).
+    torch.float32 forces exact fp32 partials for any table.
+
+    A peer that never signals makes the waiting kernel give up after the peer
+    timeout (default 60 s, set_peer_timeout_ms): the affected output / gather
+    slice is filled with NaN and the next call on this object raises.
     """
 
     def __init__(self, local_table: torch.Tensor, num_rows: int,
                  group: Optional[dist.ProcessGroup] = None,
-                 partial_dtype: torch.dtype = torch.float32,
+                 partial_dtype: Optional[torch.dtype] = None,
                  rank: Optional[int] = None, world: Optional[int] = None,
                  buffers: Optional[Callable] = None):
         if not local_table.is_cuda:
@@ -75,7 +83,7 @@ class PeerShardedEmbedding:
                              f"local table has {local_table.shape[0]} rows")
         self.table = local_table
         self.device = local_table.device
-        self.partial_dtype = partial_dtype
+        self.partial_dtype = local_table.dtype if partial_dtype is None else partial_dtype
         self.ops = CudaLocalOps()
         self._lib = _lib.load()
         self._buffers = buffers if buffers is not None else \
@@ -85,6 +93,13 @@ class PeerShardedEmbedding:
         self._side = torch.cuda.Stream(device=self.device)
         self._flags = self._buffers("flags", peer.FLAG_BYTES)
         self._flag_ptrs = peer.ptr_array(self._flags.ptrs)
+        # one step in flight per channel: the exchange buffers are two deep (epoch
+        # parity), which only protects begin(e) / finish(e) / begin(e+1) / ...
+        self._pending = {CH_FORWARD: False, CH_GRAD: False, CH_CONCAT: False}
+        # asynchronous read-back of the wait status (checked one call later, so
+        # the data path never synchronises with the host)
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._status_event = None
 
     # ------------------------------------------------------------ plumbing
     def _buffer(self, kind: str, nbytes: int):
@@ -100,10 +115,44 @@ class PeerShardedEmbedding:
         _check(self._lib.cuembed_shard_signal(self._flag_ptrs, self.world, self.rank,
                                               channel, epoch, _stream(stream)))
 
-    def status(self) -> int:
-        """0, or 1 + the rank a wait gave up on (needs a prior synchronize)."""
+    def _status_tensor(self) -> torch.Tensor:
         word = peer.CHANNELS * peer.MAX_WORLD
-        return int(self._flags.tensor(4 * word, (1,), torch.int32).item())
+        return self._flags.tensor(4 * word, (1,), torch.int32)
+
+    def status(self) -> int:
+        """0, or 1 + the rank a wait gave up on (synchronises)."""
+        return int(self._status_tensor().item())
+
+    def set_peer_timeout_ms(self, timeout_ms: int) -> None:
+        """Process-wide: how long a wait spins before it gives up."""
+        _check(self._lib.cuembed_shard_set_timeout_ms(int(timeout_ms)))
+
+    def _begin(self, channel: int) -> None:
+        self._raise_on_timeout()
+        if self._pending[channel]:
+            raise CuEmbedError(
+                "a step of this channel is still in flight: call *_finish before the "
+                "next *_begin (the peer exchange buffers are two epochs deep)")
+        self._pending[channel] = True
+
+    def _finish(self, channel: int, stream=None) -> None:
+        """After the waiting kernel of a step: queue the status read-back."""
+        self._pending[channel] = False
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        if isinstance(s, torch.cuda.Stream):
+            with torch.cuda.stream(s):
+                self._status_host.copy_(self._status_tensor(), non_blocking=True)
+                self._status_event = torch.cuda.Event()
+                self._status_event.record(s)
+
+    def _raise_on_timeout(self) -> None:
+        ev = self._status_event
+        if ev is not None and ev.query():
+            code = int(self._status_host.item())
+            if code != 0:
+                raise CuEmbedError(
+                    f"rank {self.rank}: a peer wait timed out waiting for rank {code - 1}; "
+                    f"the affected results were filled with NaN")
 
     def close(self) -> None:
         for buf in self._bufs.values():
@@ -134,6 +183,7 @@ class PeerShardedEmbedding:
             return self._concat_begin(indices, offsets, weights, batch_size, num_hots,
                                       stream)
         lib = self._lib
+        self._begin(CH_FORWARD)
         width = self.table.shape[1]
         per = batch_size // self.world
         out_dtype = self.table.dtype if out_dtype is None else out_dtype
@@ -174,6 +224,7 @@ class PeerShardedEmbedding:
             num_hots, self.rank * per, _dev(weights, "weights"),
             _dt(weights) if weights is not None else 0, _dev(out, "out"), _dt(out),
             _stream(stream)))
+        self._finish(CH_FORWARD, stream)
         return out, ctx
 
     def _concat_begin(self, indices, offsets, weights, batch_size, num_hots, stream):
@@ -182,6 +233,7 @@ class PeerShardedEmbedding:
         if offsets is not None or num_hots <= 0:
             raise CuEmbedError("Check failed: offsets == nullptr || mode != CombineMode::kConcat")
         lib = self._lib
+        self._begin(CH_CONCAT)
         width = self.table.shape[1]
         per = batch_size // self.world
         one = per * num_hots * width * self.table.element_size()
@@ -204,8 +256,11 @@ class PeerShardedEmbedding:
         width = self.table.shape[1]
         per = ctx.batch // self.world
         num_hots = ctx.num_hots
+        one = per * num_hots * width * self.table.element_size()
         _check(lib.cuembed_shard_wait(self._flags.local, self.world, CH_CONCAT, epoch,
+                                      buf.local + base, one // self.world,
                                       _stream(stream)))
+        self._finish(CH_CONCAT, stream)
         # valid until the next-but-one concat forward (double buffer)
         out = buf.tensor(base, (per * num_hots, width), self.table.dtype)
         return out, ctx
@@ -254,6 +309,7 @@ class PeerShardedEmbedding:
         """Push phase: copy engines send the slice to every rank (side stream)
         while the main stream selects and sorts; never waits for another rank."""
         lib = self._lib
+        self._begin(CH_GRAD)
         grad_out_slice = grad_out_slice.contiguous()
         width = grad_out_slice.shape[1]
         n_slice = grad_out_slice.shape[0]
@@ -285,8 +341,11 @@ class PeerShardedEmbedding:
         n_slice = grad_out_slice.shape[0]
         main = torch.cuda.current_stream(self.device)
         _check(lib.cuembed_shard_wait(self._flags.local, self.world, CH_GRAD, epoch,
+                                      buf.local + base,
+                                      n_slice * width * grad_out_slice.element_size(),
                                       main.cuda_stream))
         main.wait_stream(self._side)  # the local slice was copied on the side stream
+        self._finish(CH_GRAD, main)
         if ctx.local_nnz == 0:
             rows = 0 if compressed else self.hi - self.lo
             idt = ctx.indices.dtype

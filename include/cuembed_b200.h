@@ -332,9 +332,18 @@ int cuembed_shard_concat_push(const void* local_params, int dtype,
  * after the pushing kernel / copies on the same stream). */
 int cuembed_shard_signal(void* const* flag_ptrs, int world, int rank,
                          int channel, unsigned epoch, cuembed_stream_t stream);
-/* Hold the stream until all ranks signalled `epoch` on `channel`. */
+/* Hold the stream until all ranks signalled `epoch` on `channel`.  A wait
+ * gives up after the peer timeout (default 60 s, CUEMBED_PEER_TIMEOUT_MS or
+ * cuembed_shard_set_timeout_ms): the status word (4 bytes at
+ * flags + CUEMBED_PEER_CHANNELS * CUEMBED_MAX_WORLD words) then holds 1 + the
+ * missing rank, and -- so that stale data never passes for a result -- slice
+ * [rank] of `poison` ([world] slices of poison_bytes; may be NULL) is filled
+ * with 0xff bytes (NaN in every element type).  cuembed_shard_reduce_finalize
+ * poisons its whole output the same way. */
 int cuembed_shard_wait(const void* flags, int world, int channel,
-                       unsigned epoch, cuembed_stream_t stream);
+                       unsigned epoch, void* poison, size_t poison_bytes,
+                       cuembed_stream_t stream);
+int cuembed_shard_set_timeout_ms(long long timeout_ms);
 
 /*
  * Forward, step 2 (on the bag owner): wait for all ranks, then
@@ -358,6 +367,19 @@ int cuembed_shard_reduce_finalize(const void* slots, int partial_dtype,
 int cuembed_shard_allgather_push(const void* src, size_t bytes,
                                  void* const* gather_ptrs, int world, int rank,
                                  cuembed_stream_t stream);
+
+/*
+ * Diagnostics: measured gather ceiling for the roofline (csrc/microbench.cu).
+ * Gathers n rows of row_bytes (128, 256 or 512) at rows[i] * row_bytes from
+ * buf with the access shape of the forward / backward kernels (lane group per
+ * row, 16-byte loads, 8 rows in flight, persistent grid) and no arithmetic
+ * beyond one XOR per word.  On an L2-resident buffer this is the L2 -> SM
+ * gather ceiling, on a multi-GB buffer the DRAM gather ceiling.
+ * no_l1_allocate != 0 uses ld.global.nc.L1::no_allocate.  sink: 4 bytes.
+ */
+int cuembed_microbench_gather(const void* buf, int row_bytes, const int* rows,
+                              long long n, int no_l1_allocate, unsigned* sink,
+                              cuembed_stream_t stream);
 
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */

@@ -20,8 +20,22 @@ WANT = {
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "ld_sectors",
     "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum": "ld_requests",
+    # L2 -> SM side (what bounds the gather kernels)
+    "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors_from_sm",
+    "l1tex__m_xbar2l1tex_read_bytes.sum": "xbar_to_l1_read_bytes",
+    "derived__lts__lts2xbar_bytes.sum": "l2_to_xbar_bytes",
+    "derived__lts__lts2xbar_bytes.sum.per_second": "l2_to_xbar_bytes_per_s",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_pct",
+    "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed": "l1_writeback_pct",
+    "lts__t_sector_throughput_srcunit_tex.avg.pct_of_peak_sustained_elapsed": "l2_tex_sector_tput_pct",
+    "smsp__inst_executed.sum": "warp_instructions",
+    "sm__cycles_elapsed.max": "sm_cycles",
 }
-SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0, "ns": 1e-3, "us": 1.0,
+         "ms": 1e3, "Gbyte/s": 1e9, "Tbyte/s": 1e12, "Mbyte/s": 1e6}
+import re
+STALL = re.compile(r"smsp__average_warps?_issue_stalled_(\w+)_per_issue_active\.ratio$|"
+                   r"smsp__average_warp_latency_issue_stalled_(\w+)\.ratio$")
 out = {}
 for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", "prof_*.ncu-rep"))):
     name = os.path.basename(rep)[5:-8]
@@ -29,7 +43,14 @@ for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", "prof_*.ncu-rep")))
     rows = list(csv.reader(txt.splitlines()))
     hdr, unit, vals = rows[0], rows[1], rows[2]
     d = {"kernel": vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else name}
+    stalls = {}
     for i, h in enumerate(hdr):
+        m = STALL.match(h)
+        if m:
+            try:
+                stalls[m.group(1) or m.group(2)] = round(float(vals[i]), 3)
+            except ValueError:
+                pass
         if h in WANT:
             try:
                 v = float(vals[i])
@@ -37,17 +58,27 @@ for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", "prof_*.ncu-rep")))
                 continue
             v *= SCALE.get(unit[i], 1.0)
             d[WANT[h]] = v
+    if stalls:
+        # warps stalled per issued instruction, by reason (largest first)
+        d["warp_stalls_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
     if "dram_read" in d and "dram_write" in d:
         d["dram_bytes"] = d["dram_read"] + d["dram_write"]
     if d.get("ld_requests"):
         d["sectors_per_request"] = d["ld_sectors"] / d["ld_requests"]
     out[name] = d
+try:
+    out["commit"] = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"],
+                                   capture_output=True, text=True).stdout.strip()
+except OSError:
+    pass
 os.makedirs(os.path.join(root, "profiles"), exist_ok=True)
 path = os.path.join(root, "profiles", f"{tag}_ncu_summary.json")
 json.dump(out, open(path, "w"), indent=1)
 print("| kernel | dur us | DRAM MB (r+w) | L2 hit % | L1 hit % | occ % | regs | IPC | issue % | L2 tput % | DRAM tput % | sect/req |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|")
 for k, d in out.items():
+    if not isinstance(d, dict):
+        continue
     print(f"| {k} | {d.get('duration_us',0):.1f} | {d.get('dram_bytes',0)/1e6:.1f} | {d.get('l2_hit_pct',0):.1f} | "
           f"{d.get('l1_hit_pct',0):.1f} | {d.get('achieved_occupancy_pct',0):.1f} | {int(d.get('registers',0))} | "
           f"{d.get('ipc',0):.2f} | {d.get('issue_active_pct',0):.1f} | {d.get('l2_throughput_pct',0):.1f} | "

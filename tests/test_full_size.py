@@ -165,6 +165,58 @@ def test_backward_full_size_exact_and_idempotent(c2):
     assert torch.equal(table, -(2.0 ** -6) * want_t)
 
 
+def test_backward_full_gradient_beyond_2_31_elements(c2):
+    """Full (uncompressed) gradient at the headline shape: 10 M x 256 fp16 =
+    2.56 G elements (5.12 GB), i.e. element offsets beyond 2^31.  The reference
+    addresses gradient rows with `int` arithmetic
+    (cuembed/include/embedding_lookup_ops.cuh:610-618) and overflows here; this
+    library uses 64-bit byte offsets.  Integer gradients: every sum is exact in
+    fp32, so the result must equal torch's index_add bit for bit, rows that no
+    lookup touches must be zero (skip_grad_init = false) and a poisoned buffer
+    must keep its poison there (skip_grad_init = true)."""
+    _, indices, grad_y = c2
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~40 GB of device memory")
+    nnz = BATCH * HOT
+    assert ROWS * WIDTH >= 2 ** 31
+    row_ids = torch.empty(nnz, dtype=torch.int32, device=DEV)
+    ce.ExtractRowIdsFromFixed(BATCH, HOT, row_ids)
+    t_idx = torch.empty_like(indices)
+    t_sid = torch.empty_like(indices)
+    work = torch.empty(ce.Transpose(row_ids, indices, None, nnz, None, None, None, None),
+                       dtype=torch.uint8, device=DEV)
+    ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+    grad = torch.full((ROWS, WIDTH), float("nan"), dtype=torch.float16, device=DEV)
+    ce.EmbeddingBackward(grad_y, WIDTH, ROWS, nnz, t_idx, t_sid, None, None, False, grad, None)
+    torch.cuda.synchronize()
+    want = torch.zeros(ROWS, WIDTH, dtype=torch.float32, device=DEV)
+    for n0 in range(0, nnz, 1 << 19):
+        n1 = min(nnz, n0 + (1 << 19))
+        want.index_add_(0, t_idx[n0:n1].long(), grad_y[t_sid[n0:n1].long()].float())
+    assert float(want.abs().max()) < 2 ** 24
+    want16 = want.half()
+    del want
+    # rows in the upper half of the table lie beyond element offset 2^31
+    touched_high = int((t_idx.long() * WIDTH >= 2 ** 31).sum())
+    assert touched_high > nnz // 4
+    for r0 in range(0, ROWS, 1 << 21):  # chunked compare keeps the peak memory low
+        r1 = min(ROWS, r0 + (1 << 21))
+        assert torch.equal(grad[r0:r1], want16[r0:r1]), f"rows {r0}..{r1}"
+    # skip_grad_init: untouched rows keep their previous contents
+    grad.fill_(7.0)
+    ce.EmbeddingBackward(grad_y, WIDTH, ROWS, nnz, t_idx, t_sid, None, None, True, grad, None)
+    torch.cuda.synchronize()
+    touched = torch.zeros(ROWS, dtype=torch.bool, device=DEV)
+    touched[t_idx.long()] = True
+    for r0 in range(0, ROWS, 1 << 21):
+        r1 = min(ROWS, r0 + (1 << 21))
+        t = touched[r0:r1, None]
+        assert torch.equal(grad[r0:r1], torch.where(t, want16[r0:r1], torch.full_like(want16[r0:r1], 7.0)))
+    del grad, want16
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------- C3 shapes
 def test_c3_csr_weighted_int64_full_size_exact():
     """BASELINE.json configs[2]: CSR bags of U{0..64} lookups (mean 32), weighted

@@ -158,12 +158,47 @@ def _combos():
             (BF16, np.int32, False), (BF16, np.int64, True)]
 
 
+@pytest.fixture(params=["oracle", "ref"])
+def checker(request):
+    """The CPU side of the comparison: the C restatement (oracle/) and, one hop
+    closer, the reference's own CPU templates compiled from /root/reference
+    (oracle/_ref/libcuembed_ref.so, prebuilt; travels with the tree)."""
+    return request.getfixturevalue("oracle" if request.param == "oracle" else "reflib")
+
+
+def test_c1_exact_shape_against_reference_cpu(cuda_lib, reflib):
+    """BASELINE.json configs[0] at its own shape: 1 M categories x 32 fp32, batch
+    1024, fixed hotness 8, sum (the test_embedding_against_cpu path), checked
+    against the reference's CPU templates: forward, transpose, compressed and
+    full backward, all bit-exact."""
+    for compressed in (True, False):
+        p = Problem(1024, 32, 8, "sum", compressed=compressed, num_categories=1_048_576,
+                    dt=F32, index_dtype=np.int32, alpha=0.0, seed=31)
+        want = p.cpu_forward(reflib)
+        got = gh.gpu_forward(p)
+        assert bits_equal(got, want), _diff(got, want, "C1 forward")
+        rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
+        c_rows, c_idx, c_sid, c_w, c_remapped = p.cpu_transpose(reflib)
+        assert np.array_equal(rows.cpu().numpy(), c_rows)
+        assert np.array_equal(t_idx.cpu().numpy(), c_idx)
+        assert np.array_equal(t_sid.cpu().numpy(), c_sid)
+        if compressed:
+            assert np.array_equal(remapped.cpu().numpy(), c_remapped)
+        (c_grad, c_inv), _ = p.cpu_backward(reflib, c_idx, c_sid, c_w, c_remapped)
+        g_grad, g_inv, _ = gh.gpu_backward(p, t_idx, t_sid, t_w, remapped)
+        assert bits_equal(g_grad, c_grad), _diff(g_grad, c_grad, "C1 backward")
+        if compressed:
+            assert np.array_equal(g_inv, c_inv)
+
+
 @pytest.mark.parametrize("case", range(57))
-def test_against_cpu_matrix(cuda_lib, oracle, case):
+def test_against_cpu_matrix(cuda_lib, checker, case):
     """Forward, Transpose and Backward on the 57 option sets of
-    tests/test_embedding_against_cpu.cu:236-293.  Stricter than the reference's
+    tests/test_embedding_against_cpu.cu:236-293, against the C restatement AND
+    against the reference's own CPU templates.  Stricter than the reference's
     own checks (:153-218): everything bit-exact, including weighted forward and
     the order of sample ids / weights inside a row."""
+    oracle = checker
     shape = kat.against_cpu_matrix()[case]
     combos = _combos()
     big = shape["batch"] * shape["width"] * shape["hot"] >= 1_000_000

@@ -214,6 +214,94 @@ def test_virtual_ranks_16bit_partials(cuda_lib, oracle):
 
 
 @pytest.mark.gpu
+def test_default_partial_type_is_the_table_type(cuda_lib, oracle):
+    """fp16 / bf16 tables put 16-bit partial sums on the wire by default (half
+    the NVLink bytes), fp32 tables fp32 partials.  Stated tolerance of the
+    16-bit default against the fp32-accumulating oracle: every one of the
+    `world` partials is rounded once to the 16-bit type before the rank-ordered
+    fp32 reduction, i.e. |error| <= world * 2^-11 (fp16; 2^-8 for bf16) of the
+    largest partial, plus the final rounding of the output."""
+    for dt, eps in ((F16, 2.0 ** -11), (helpers.BF16, 2.0 ** -8)):
+        p = Problem(64, 128, 32, "sum", num_categories=2000, dt=dt, alpha=1.15, seed=66,
+                    compressed=True)
+        world = 4
+        outs, grads, rows, _ = run_virtual(p, world, oracle, partial_dtype=None)[0]
+        got = np.concatenate([to_f32(o) for o in outs])
+        ref = to_f32(p.cpu_forward(oracle, out_dt=F32))
+        scale = np.maximum(1.0, np.abs(ref))
+        assert np.all(np.abs(got - ref) <= (world + 1) * eps * 4 * scale)
+        check_backward(p, world, oracle, grads, rows)  # gradients never touch the partials
+
+
+@pytest.mark.gpu
+def test_missing_peer_poisons_the_result_and_raises(cuda_lib):
+    """A rank that never signals: the waiting kernel gives up after the peer
+    timeout, fills the output with NaN instead of summing stale slots, and the
+    next call on the object raises (silent stale sums)."""
+    import gpu_helpers as gh
+    from cuembed_b200 import peer
+    from cuembed_b200.api import CuEmbedError
+    from cuembed_b200.sharded_p2p import PeerShardedEmbedding
+    dev = torch.device(gh.DEV)
+    world = 2
+    group = peer.LocalPeerGroup(world, dev)
+    shared = {}
+
+    def factory(rank):
+        def make(kind, nbytes):
+            key = (kind, nbytes)
+            if key not in shared:
+                shared[key] = group.alloc(nbytes)
+            return shared[key][rank]
+        return make
+
+    table = torch.ones(100, 32, dtype=torch.float32, device=dev)
+    embs = [PeerShardedEmbedding(table[r * 50:(r + 1) * 50].contiguous(), 100, rank=r,
+                                 world=world, buffers=factory(r)) for r in range(world)]
+    idx = torch.randint(0, 100, (8 * 4,), dtype=torch.int32, device=dev)
+    try:
+        embs[0].set_peer_timeout_ms(200)
+        # only rank 0 runs the step: rank 1's signal never arrives
+        out, _ = embs[0].forward(idx, None, None, 8, 4, CombineMode.kSum)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(out).all()), "stale slots were summed"
+        assert embs[0].status() == 2  # 1 + the missing rank
+        with pytest.raises(CuEmbedError, match="timed out"):
+            embs[0].forward(idx, None, None, 8, 4, CombineMode.kSum)
+    finally:
+        embs[0].set_peer_timeout_ms(60000)
+        torch.cuda.synchronize()
+        for e in embs:
+            e.close()
+
+
+@pytest.mark.gpu
+def test_second_begin_before_finish_is_refused(cuda_lib):
+    """The exchange buffers are two epochs deep: a second forward_begin while
+    the first is unfinished could overwrite slots a slower peer still reduces
+    (ADVICE r1); the object refuses it."""
+    import gpu_helpers as gh
+    from cuembed_b200 import peer
+    from cuembed_b200.api import CuEmbedError
+    from cuembed_b200.sharded_p2p import PeerShardedEmbedding
+    dev = torch.device(gh.DEV)
+    group = peer.LocalPeerGroup(1, dev)
+    table = torch.ones(10, 32, dtype=torch.float32, device=dev)
+    emb = PeerShardedEmbedding(table, 10, rank=0, world=1,
+                               buffers=lambda kind, nbytes: group.alloc(nbytes)[0])
+    idx = torch.zeros(8, dtype=torch.int32, device=dev)
+    try:
+        pend = emb.forward_begin(idx, None, None, 4, 2, CombineMode.kSum)
+        with pytest.raises(CuEmbedError, match="in flight"):
+            emb.forward_begin(idx, None, None, 4, 2, CombineMode.kSum)
+        out, _ = emb.forward_finish(pend)
+        torch.cuda.synchronize()
+        assert torch.equal(out, torch.full((4, 32), 2.0, device=dev))
+    finally:
+        emb.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world,dt,it", [(2, F32, np.int32), (4, F16, np.int64)])
 def test_virtual_ranks_concat(cuda_lib, oracle, world, dt, it):
     p = Problem(32, 48, 6, "concat", compressed=True, num_categories=301, dt=dt,
@@ -244,7 +332,8 @@ def _two_gpu_worker(rank, world, port, results):
                     dt=F16, alpha=1.15, seed=71)
         lo, hi = row_range(p.num_categories, world, rank)
         table = torch.from_numpy(p.table[lo:hi].copy()).to(dev)
-        emb = PeerShardedEmbedding(table, p.num_categories)
+        # fp32 partials: bit-exact against the rank-ordered restatement below
+        emb = PeerShardedEmbedding(table, p.num_categories, partial_dtype=torch.float32)
         idx = torch.from_numpy(p.indices).to(dev)
         off = torch.from_numpy(p.offsets).to(dev)
         per = p.batch // world
