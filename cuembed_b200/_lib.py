@@ -73,7 +73,9 @@ SIGNATURES = {
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # CUEMBED_B200_LIB: a differently tuned build of the same sources (kernel
+    # tuning sweeps under gpurun); the default is the in-tree product library
+    return os.environ.get("CUEMBED_B200_LIB") or _build.LIB_PATH
 
 
 def load() -> ctypes.CDLL:

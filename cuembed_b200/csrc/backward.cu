@@ -70,6 +70,7 @@ struct BwdArgs {
   int sm_slots;
   // fused sparse optimizer step: opt_kind != 0 makes `grad`
   // the TABLE and every finished row sum an in-place update of its table row
+  int warp_path;     // rows that one warp covers: BwdWarpKernel (backward_warp.cuh)
   int opt_kind;      // CUEMBED_OPT_NONE / SGD / ADAGRAD
   float opt_lr;
   float opt_eps;
@@ -260,6 +261,7 @@ __device__ __forceinline__ void ApplyUpdateVec(
 
 }  // namespace cuembed_b200
 #include "backward_hot.cuh"
+#include "backward_warp.cuh"
 namespace cuembed_b200 {
 
 // FUSED_OPT: CUEMBED_OPT_NONE (write the gradient), _SGD (vector reductions
@@ -801,7 +803,13 @@ void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
     }
   }
   dim3 grid(a.num_ctas, col_tiles);
-  if (a.opt_kind == CUEMBED_OPT_ADAGRAD)
+  if (a.warp_path && a.opt_kind == CUEMBED_OPT_SGD)
+    BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_SGD>
+        <<<grid, kBwdThreads, 0, stream>>>(a);
+  else if (a.warp_path && a.opt_kind == CUEMBED_OPT_NONE)
+    BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_NONE>
+        <<<grid, kBwdThreads, 0, stream>>>(a);
+  else if (a.opt_kind == CUEMBED_OPT_ADAGRAD)
     BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4, CUEMBED_OPT_ADAGRAD>
         <<<grid, kBwdThreads, 0, stream>>>(a);  // 4: room for the old rows
   else if (a.opt_kind == CUEMBED_OPT_SGD)
@@ -946,7 +954,17 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   // a misaligned call uses narrower vectors, i.e. fewer, wider lane groups.
   RowShape shape;
   MakeRowShape(embed_width, dtype, &shape);
-  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes, dtype);
+  // Rows that a warp covers exactly (32 lanes x 4 / 8 / 16 bytes, wider rows in
+  // column tiles) take the warp-uniform walker (backward_warp.cuh).
+  static const int warp_env = EnvInt("CUEMBED_BWD_WARP", 1);
+  const int warp_vec =
+      warp_env == 0 ? 0
+                    : (row_bytes == 128 ? 4
+                                        : (row_bytes == 256
+                                               ? 8
+                                               : (row_bytes % 512 == 0 ? 16 : 0)));
+  const BwdLayout L =
+      MakeBwdLayout(nnz, embed_width, warp_vec != 0 ? 32 : shape.lanes, dtype);
   if (work == nullptr) {
     *lwork = L.total;
     return CUEMBED_OK;
@@ -979,6 +997,12 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
                         static_cast<uint64_t>(row_bytes);
   while (v > 4 && (bits % v) != 0) v /= 2;
   if ((bits % v) != 0) return CUEMBED_ERR_ARGUMENT;
+  // warp path: its vector width must be allowed by the pointers (otherwise the
+  // generic kernel runs with narrower vectors, i.e. 32 lanes as well, so the
+  // layout sized above still fits)
+  const bool warp_path = warp_vec != 0 && (bits % warp_vec) == 0 &&
+                         opt.kind != CUEMBED_OPT_ADAGRAD;
+  if (warp_path) v = warp_vec;
 
   BwdArgs a;
   a.grad_y = grad_y;
@@ -1007,6 +1031,7 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   a.cta_nz = L.cta_nz;
   a.num_ctas = L.num_ctas;
   a.num_chunks = L.num_ctas * (kBwdThreads / a.lanes);
+  a.warp_path = warp_path ? 1 : 0;
   a.opt_kind = opt.kind;
   a.opt_lr = opt.lr;
   a.opt_eps = opt.eps;

@@ -1,0 +1,276 @@
+// backward_warp.cuh -- the chunk walker of the backward for rows that one warp
+// covers exactly (row bytes 128, 256 or a multiple of 512: 32 lanes x 4 / 8 /
+// 16 bytes, wider rows in column tiles).  Included by backward.cu.
+//
+// Same contract as BwdSegReduceKernel (chunk = K consecutive nonzeros of the
+// sorted COO, walked in order with fp32 accumulators; runs inside the chunk are
+// rounded once and stored; a run that crosses chunk edges leaves a head and / or
+// tail partial for the fix-up), but with ONE lane group per warp every
+// condition is warp-uniform, which removes most of the instructions ncu counted
+// per nonzero in round 1 (~30 per nonzero on average, ~40 on cold rows):
+//
+//   * the row address is ONE IMAD.WIDE (sample id x row pitch + a base pointer
+//     that already contains the lane's column offset and is kept opaque to the
+//     compiler, which otherwise re-adds the kernel-parameter base per load);
+//   * the batches of a round are fully unrolled, so every shuffle has an
+//     immediate source lane;
+//   * run ends come from a shuffle of the keys (no second key load per lane);
+//   * inverse_mapping is written by the lanes that own a run end, once per
+//     round of 32 nonzeros, instead of two shuffles + a store per run end;
+//   * a run of length one (74 % of the runs at the headline workload) is a row
+//     COPY: the loaded vector is stored after a 16-bit "+ 0" (which gives the
+//     -0 -> +0 of the oracle's `0 + x`), skipping 8 mixed-precision adds, 4
+//     packs and the accumulator reset;
+//   * a batch of 8 nonzeros without a run end is 8 x (shuffle, address, load)
+//     + 64 adds and nothing else.
+#ifndef CUEMBED_B200_CSRC_BACKWARD_WARP_CUH_
+#define CUEMBED_B200_CSRC_BACKWARD_WARP_CUH_
+
+namespace cuembed_b200 {
+
+#ifndef BWD_WARP_MINB
+#define BWD_WARP_MINB 6
+#endif
+
+// round_T(0.f + float(x)) for every 16-bit element of a vector: x itself except
+// that -0 becomes +0 (what a sum that starts at +0 gives).
+template <typename T, int V>
+__device__ __forceinline__ typename VecBits<V>::type ZeroPlus(
+    typename VecBits<V>::type v) {
+  static_assert(sizeof(T) == 2, "16-bit element types only");
+  constexpr int NW = V / 4;
+  uint32_t w[NW];
+  Unpack32(v, w);
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    if constexpr (Elem<T>::kCode == CUEMBED_F16)
+      asm("add.rn.f16x2 %0, %1, %2;" : "=r"(w[i]) : "r"(w[i]), "r"(0u));
+    else
+      asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(w[i]) : "r"(w[i]), "r"(0u));
+  }
+  typename VecBits<V>::type out;
+  Pack32(w, &out);
+  return out;
+}
+
+template <typename IdxT>
+__device__ __forceinline__ IdxT ShflDownIdx(IdxT v, int delta) {
+  if constexpr (sizeof(IdxT) == 8)
+    return static_cast<IdxT>(
+        __shfl_down_sync(0xffffffffu, static_cast<long long>(v), delta));
+  else
+    return __shfl_down_sync(0xffffffffu, v, delta);
+}
+
+template <typename T>
+__device__ __forceinline__ float ShflWeight(T w, int src) {
+  if constexpr (sizeof(T) == 4) {
+    return __shfl_sync(0xffffffffu, w, src);
+  } else {
+    const unsigned short b = *reinterpret_cast<const unsigned short*>(&w);
+    const unsigned rb = __shfl_sync(0xffffffffu, static_cast<unsigned>(b), src);
+    const unsigned short rs = static_cast<unsigned short>(rb);
+    return Elem<T>::ToFloat(*reinterpret_cast<const T*>(&rs));
+  }
+}
+
+// FUSED_OPT: CUEMBED_OPT_NONE or CUEMBED_OPT_SGD (Adagrad stays on the generic
+// kernel: it needs the old table rows in flight).
+template <typename T, int V, typename IdxT, bool WEIGHTED, int FUSED_OPT>
+__global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
+    BwdWarpKernel(const BwdArgs a) {
+  using VecT = typename VecBits<V>::type;
+  constexpr int NW = V / 4;
+  constexpr int NE = NW * Elem<T>::kPerWord;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int UNROLL = 8;
+  constexpr bool kCopySingles =
+      !WEIGHTED && FUSED_OPT == CUEMBED_OPT_NONE && sizeof(T) == 2;
+
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
+  const IdxT* __restrict__ keys = static_cast<const IdxT*>(a.keys);
+  const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
+  const T* __restrict__ weights = static_cast<const T*>(a.weights);
+  const IdxT* __restrict__ tidx = static_cast<const IdxT*>(a.tidx);
+  const uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+
+  const int K = a.chunk_nz;
+  const int64_t c0 = static_cast<int64_t>(chunk) * K;
+  int n = 0;
+  if (c0 < a.nnz) n = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
+  // A chunk of a hot unit is summed by the hot-row kernels: nothing to walk
+  // here, it only reports itself as a "through" chunk.
+  const bool hot_chunk =
+      a.chunk_state != nullptr && a.chunk_state[chunk] == kChunkHot;
+  if (hot_chunk) n = 0;
+
+  const int v = blockIdx.y * 32 + lane;
+  const bool active = v < a.nvec;
+  // base pointers that already hold this lane's column offset; opaque so that
+  // a row address is one IMAD.WIDE (index x pitch + base)
+  const char* gy = static_cast<const char*>(a.grad_y) +
+                   static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  char* out = static_cast<char*>(a.grad) + static_cast<int64_t>(active ? v : 0) * V;
+  asm volatile("" : "+l"(gy), "+l"(out));
+  float* __restrict__ my_head =
+      a.scratch + (static_cast<size_t>(chunk) * 2 + 0) * a.width;
+  float* __restrict__ my_tail =
+      a.scratch + (static_cast<size_t>(chunk) * 2 + 1) * a.width;
+
+  // Does the first run continue a run of the previous chunk; does the last
+  // element end its run?  (uniform loads)
+  bool cont = false;
+  bool last_is_end = true;
+  if (n > 0) {
+    if (c0 > 0) cont = __ldg(keys + c0 - 1) == __ldg(keys + c0);
+    if (c0 + n < a.nnz)
+      last_is_end = __ldg(keys + c0 + n) != __ldg(keys + c0 + n - 1);
+  }
+  bool in_first = true;
+  bool open = false;
+  int head_kind = kHeadNone;
+  IdxT head_row = 0;
+
+  float acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+
+  // (key, sample, weight) of a round are requested one round ahead.
+  IdxT key_n = 0, sid_n = 0;
+  T w_n = T();
+  auto request = [&](int r) {
+    key_n = 0;
+    sid_n = 0;
+    w_n = T();
+    const int p = r * 32 + lane;
+    if (p < n) {
+      key_n = __ldg(keys + c0 + p);
+      sid_n = __ldg(sids + c0 + p);
+      if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + p);
+    }
+  };
+  request(0);
+
+  auto flush = [&](IdxT krow) {
+    if (in_first && cont) {
+      // Run began in an earlier chunk: partial, added by the fix-up.
+      if (active) StorePartial<NE>(my_head + v * NE, acc);
+      head_kind = kHeadEnds;
+      head_row = krow;
+    } else if (active) {
+      char* dst = RowAddr<IdxT>(out, krow, row_bytes);
+      if constexpr (FUSED_OPT == CUEMBED_OPT_NONE)
+        StoreFloatsAs<NE>(dst, 0, Elem<T>::kCode, acc);
+      else
+        ApplyUpdateVec<T, V, NE>(a, dst - static_cast<int64_t>(v) * V,
+                                 static_cast<int64_t>(krow),
+                                 static_cast<int64_t>(v) * NE, acc, VecT());
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+    in_first = false;
+    open = false;
+  };
+
+#pragma unroll 1
+  for (int r = 0; r * 32 < n; ++r) {
+    const int cnt = min(32, n - r * 32);
+    const int p = r * 32 + lane;
+    const IdxT key = key_n, sid = sid_n;
+    const T w = w_n;
+    request(r + 1);
+    // run ends of this round: the next key is one lane to the right, the first
+    // key of the next round for lane 31, `last_is_end` for the chunk's last
+    IdxT knext = ShflDownIdx<IdxT>(key, 1);
+    const IdxT kfirst = ShflIdx<IdxT>(key_n, 0, 32);
+    if (lane == 31) knext = kfirst;
+    const bool end = p < n && (p == n - 1 ? last_is_end : knext != key);
+    const unsigned endsw = __ballot_sync(kFull, end);
+    // inverse_mapping: the lane that owns a run end writes it (load issued now,
+    // store after the row loop so that nothing waits for it)
+    const bool write_inv =
+        end && a.inverse_mapping != nullptr && blockIdx.y == 0;
+    IdxT tk = 0;
+    if (write_inv) tk = __ldg(tidx + c0 + p);
+
+#pragma unroll
+    for (int jb = 0; jb < 32; jb += UNROLL) {
+      if (jb >= cnt) break;  // warp-uniform
+      VecT vals[UNROLL];
+      float wf[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        // lanes past the end of the chunk carry sample id 0: a valid,
+        // harmless load that is never accumulated
+        const IdxT s = ShflIdx<IdxT>(sid, jb + u, 32);
+        if constexpr (WEIGHTED) wf[u] = ShflWeight<T>(w, jb + u);
+        vals[u] = LdgVec<V>(RowAddr<IdxT>(gy, s, row_bytes));
+      }
+      const unsigned m8 = (endsw >> jb) & ((1u << UNROLL) - 1u);
+      if (m8 == 0u && jb + UNROLL <= cnt) {
+        // no run ends in this batch (the interior of a long run)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if constexpr (WEIGHTED)
+            AccumulateVecWeighted<T, V>(vals[u], wf[u], acc);
+          else
+            AccumulateVec<T, V>(vals[u], acc);
+        }
+        open = true;
+        continue;
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int j = jb + u;
+        if (j >= cnt) break;  // warp-uniform
+        const bool is_end = ((m8 >> u) & 1u) != 0u;
+        if constexpr (kCopySingles) {
+          if (is_end && !open && !(in_first && cont)) {
+            // a run of length one: round(0 + x) == x (-0 -> +0): row copy
+            const IdxT krow = ShflIdx<IdxT>(key, j, 32);
+            if (active)
+              StcsVec<V>(RowAddr<IdxT>(out, krow, row_bytes),
+                         ZeroPlus<T, V>(vals[u]));
+            in_first = false;
+            continue;
+          }
+        }
+        if constexpr (WEIGHTED)
+          AccumulateVecWeighted<T, V>(vals[u], wf[u], acc);
+        else
+          AccumulateVec<T, V>(vals[u], acc);
+        open = true;
+        if (is_end) flush(ShflIdx<IdxT>(key, j, 32));
+      }
+    }
+    if (write_inv) static_cast<IdxT*>(a.inverse_mapping)[key] = tk;
+  }
+
+  // Leftover: the last run of the chunk continues into the next chunk.
+  int has_tail = 0;
+  IdxT tail_row = 0;
+  if (open) {
+    if (in_first && cont) {
+      head_kind = kHeadThrough;
+      if (active) StorePartial<NE>(my_head + v * NE, acc);
+    } else {
+      has_tail = 1;
+      tail_row = __ldg(keys + c0 + n - 1);
+      if (active) StorePartial<NE>(my_tail + v * NE, acc);
+    }
+  }
+  if (hot_chunk) head_kind = kHeadThrough;
+  if (lane == 0 && blockIdx.y == 0) {
+    a.meta[chunk * 2 + 0] = head_kind;
+    a.meta[chunk * 2 + 1] = has_tail;
+    a.meta_row[chunk * 2 + 0] = static_cast<long long>(head_row);
+    a.meta_row[chunk * 2 + 1] = static_cast<long long>(tail_row);
+    // work list of the fix-up (any order: every chain is summed on its own)
+    if (has_tail) a.tail_list[1 + atomicAdd(a.tail_list, 1)] = chunk;
+  }
+}
+
+}  // namespace cuembed_b200
+
+#endif  // CUEMBED_B200_CSRC_BACKWARD_WARP_CUH_

@@ -360,6 +360,31 @@ __device__ __forceinline__ void StoreFloatsAs(void* out_row, int64_t elem_off,
   }
 }
 
+// Address of row `row` of a row-major array: base + row * pitch.  Indices are
+// non-negative; with 32-bit indices this is exactly ONE instruction
+// (IMAD.WIDE.U32 with the 64-bit base as addend) -- written in PTX because the
+// compiler otherwise splits it into a wide multiply plus two adds.  `base`
+// should already contain the lane's column offset.
+template <typename IdxT>
+__device__ __forceinline__ const char* RowAddr(const char* base, IdxT row,
+                                               uint32_t pitch) {
+  if constexpr (sizeof(IdxT) == 4) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "r"(static_cast<uint32_t>(row)), "r"(pitch),
+          "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const char*>(r);
+  } else {
+    return base + static_cast<uint64_t>(row) * pitch;
+  }
+}
+template <typename IdxT>
+__device__ __forceinline__ char* RowAddr(char* base, IdxT row, uint32_t pitch) {
+  return const_cast<char*>(
+      RowAddr<IdxT>(static_cast<const char*>(base), row, pitch));
+}
+
 template <typename IdxT>
 __device__ __forceinline__ IdxT ShflIdx(IdxT v, int src, int width) {
   if constexpr (sizeof(IdxT) == 8) {

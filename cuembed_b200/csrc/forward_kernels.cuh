@@ -181,9 +181,11 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
   // store, so no load in the hot loop is predicated.
   const int v = blockIdx.y * G + lane_g;
   const bool active = v < a.nvec;
-  const char* __restrict__ params =
-      static_cast<const char*>(a.params) +
-      static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  const char* params = static_cast<const char*>(a.params) +
+                       static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  // table base + this lane's column offset in one (opaque) register pair, so a
+  // row address is a single IMAD.WIDE (common.cuh RowAddr)
+  asm volatile("" : "+l"(params));
   const IdxT* __restrict__ indices = static_cast<const IdxT*>(a.indices);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
   const uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
@@ -239,7 +241,7 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
         for (int u = 0; u < UNROLL; ++u) {
           const IdxT row = ShflIndex<IdxT>(kFull, idx_cur, jb + u, G);
           if constexpr (WEIGHTED) wv[u] = ShflElem<T>(kFull, w_cur, jb + u, G);
-          vals[u] = LdgVec<V>(params + RowOffset<IdxT>(row, row_bytes));
+          vals[u] = LdgVec<V>(RowAddr<IdxT>(params, row, row_bytes));
         }
         if (__all_sync(kFull, jb + UNROLL <= cnt)) {
 #pragma unroll

@@ -199,7 +199,7 @@ def test_backward_full_gradient_beyond_2_31_elements(c2):
     del want
     # rows in the upper half of the table lie beyond element offset 2^31
     touched_high = int((t_idx.long() * WIDTH >= 2 ** 31).sum())
-    assert touched_high > nnz // 4
+    assert touched_high > 100_000  # (hot rows sit at random places of the table)
     for r0 in range(0, ROWS, 1 << 21):  # chunked compare keeps the peak memory low
         r1 = min(ROWS, r0 + (1 << 21))
         assert torch.equal(grad[r0:r1], want16[r0:r1]), f"rows {r0}..{r1}"
