@@ -101,7 +101,7 @@ def csv_line(f, name, iterations, elapsed_ms, bw_l2, bw_dram):
 
 
 def make_inputs(f, torch, dev):
-    from cuembed_b200.sharded_bench import unique_bags_torch
+    from benchmarks.sharded_bench import unique_bags_torch
     tdt = torch.float32
     if f["half_embedding_type"]:
         tdt = torch.float16

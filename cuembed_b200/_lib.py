@@ -39,8 +39,6 @@ SIGNATURES = {
     "cuembed_backward_update": (_ci, [_vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _ci,
                                       ctypes.c_float, ctypes.c_float, _vp, _vp, _vp,
                                       _szp, _vp]),
-    "cuembed_set_backward_hot_path": (_ci, [_ci]),
-    "cuembed_backward_ws_hot_offset": (_ci, [_ci, _ci, _ci, _ci, _szp]),
     "cuembed_shard_select": (_ci, [_vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
                                    ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                    _vp, _vp, _szp, _vp]),
@@ -68,6 +66,7 @@ SIGNATURES = {
                                             _ci, _vp]),
     "cuembed_shard_allgather_push": (_ci, [_vp, _sz, ctypes.POINTER(_vp), _ci, _ci, _vp]),
     "cuembed_microbench_gather": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
+    "cuembed_microbench_gather_bulk": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }
 

@@ -308,27 +308,6 @@ def EmbeddingBackwardUpdate(grad_y: torch.Tensor, embed_width: int, nnz: int,
         _dev(work, "work"), ctypes.byref(lwork), _stream(stream)))
 
 
-def set_backward_hot_path(enable: bool) -> bool:
-    """Process-wide switch of the experimental hot-row path of the backward
-    (include/cuembed_b200.h); returns the previous setting."""
-    return bool(_lib.load().cuembed_set_backward_hot_path(1 if enable else 0))
-
-
-def backward_hot_units(work: torch.Tensor, dtype: torch.dtype, embed_width: int,
-                       nnz: int, index_dtype: torch.dtype = torch.int32) -> int:
-    """Number of hot units the last EmbeddingBackward(..., work=work) found
-    (the hot-row path); -1 if that path is off for the shape.
-    Synchronises (reads 4 bytes of the workspace)."""
-    lib = _lib.load()
-    off = ctypes.c_size_t(0)
-    _check(lib.cuembed_backward_ws_hot_offset(_DT[dtype], int(embed_width), int(nnz),
-                                              _IT[index_dtype], ctypes.byref(off)))
-    if off.value == ctypes.c_size_t(-1).value:
-        return -1
-    return int(work[off.value:off.value + 4].view(torch.int32).item())
-
-
-# ---------------------------------------------------------------- sharded mode
 def ShardSelect(indices: torch.Tensor, offsets: Optional[torch.Tensor],
                 weights: Optional[torch.Tensor], batch_size: int, num_hots: int,
                 row_lo: int, row_hi: int, local_offsets: Optional[torch.Tensor],

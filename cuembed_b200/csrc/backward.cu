@@ -59,18 +59,13 @@ struct BwdArgs {
   int cta_nz;      // nonzeros per CTA = kBwdThreads * rounds
   int num_ctas;
   int num_chunks;  // = num_ctas * lane groups per CTA
-  // hot-row path (backward_hot.cuh); chunk_state == nullptr switches it off
-  int* hot_ctr;                // [0] hot units, [1] largest sample id
-  int2* hot_units;             // [hot_cap] {first chunk, number of chunks}
-  unsigned char* chunk_state;  // [num_chunks]
-  float* hot_partial;          // [hot_cap][kHotMaxRanges][width]
-  int hot_min_chunks;
-  int hot_cap;
   int chunk_nz;  // nonzeros per chunk = lanes * rounds
   int sm_slots;
   // fused sparse optimizer step: opt_kind != 0 makes `grad`
   // the TABLE and every finished row sum an in-place update of its table row
   int warp_path;     // rows that one warp covers: BwdWarpKernel (backward_warp.cuh)
+  int own;           // warp path: run ownership across chunk edges
+  int through_split; // warp path: through chunks go to BwdThroughKernel
   int opt_kind;      // CUEMBED_OPT_NONE / SGD / ADAGRAD
   float opt_lr;
   float opt_eps;
@@ -260,7 +255,6 @@ __device__ __forceinline__ void ApplyUpdateVec(
 }
 
 }  // namespace cuembed_b200
-#include "backward_hot.cuh"
 #include "backward_warp.cuh"
 namespace cuembed_b200 {
 
@@ -304,12 +298,6 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
   int n_g = 0;
   if (c0 < a.nnz)
     n_g = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
-  // A chunk of a hot unit is summed by BwdHotKernel: nothing to walk here, it
-  // only reports itself as a "through" chunk (its head partial comes from
-  // BwdHotCombineKernel).  The lane group keeps running the warp-wide loops.
-  const bool hot_chunk =
-      a.chunk_state != nullptr && a.chunk_state[chunk] == kChunkHot;
-  if (hot_chunk) n_g = 0;
 
   const int v = blockIdx.y * G + lane_g;
   const bool active = v < a.nvec;
@@ -489,7 +477,6 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_MINB)
       if (active) StorePartial<NE>(my_tail + v * NE, acc);
     }
   }
-  if (hot_chunk) head_kind = kHeadThrough;
   if (lane_g == 0 && blockIdx.y == 0) {
     a.meta[chunk * 2 + 0] = head_kind;
     a.meta[chunk * 2 + 1] = has_tail;
@@ -676,36 +663,7 @@ struct BwdLayout {
   int num_ctas;
   int num_chunks;
   size_t scratch_off, group_off, meta_off, row_off, tail_off, total;
-  // hot-row path
-  bool hot;
-  int hot_min_chunks, hot_cap;
-  size_t hot_ctr_off, hot_units_off, state_off, hot_partial_off;
 };
-
-// Hot-row path (experimental, OFF by default: measured slower on B200, see
-// DESIGN.md 3.3): rows of 16-byte vectors up to 2 KB, and enough nonzeros for a
-// hot unit to exist at all.  cuembed_set_backward_hot_path(1) or
-// CUEMBED_BWD_HOT=1 switch it on, CUEMBED_BWD_HOT_NNZ sets the smallest hot
-// unit (nonzeros).
-std::atomic<int> g_hot_path{-1};  // -1: not decided yet (environment)
-
-int BackwardHotPathEnabled() {
-  int v = g_hot_path.load();
-  if (v < 0) {
-    v = EnvInt("CUEMBED_BWD_HOT", 0) != 0 ? 1 : 0;
-    g_hot_path.store(v);
-  }
-  return v;
-}
-
-bool HotPathShape(int embed_width, int dtype) {
-  RowShape shape;
-  if (!MakeRowShape(embed_width, dtype, &shape)) return false;
-  const int64_t row_bytes = static_cast<int64_t>(embed_width) * ElemSize(dtype);
-  // the tile kernel moves 16-byte vectors: rows the chunk walker cuts into
-  // narrower vectors (fewer than 8 x 16 bytes) stay on the chunk walker
-  return shape.vec_bytes == 16 && row_bytes <= 2048;
-}
 
 BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
   BwdLayout L;
@@ -740,69 +698,17 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
   off += AlignUp(static_cast<size_t>(L.num_chunks) * 2 * sizeof(long long), 256);
   L.tail_off = off;
   off += AlignUp(static_cast<size_t>(L.num_chunks + 1) * sizeof(int), 256);
-  const int hot_env = BackwardHotPathEnabled();
-  static const int hot_nnz = EnvInt("CUEMBED_BWD_HOT_NNZ", 2048);
-  const int chunk_nz = lanes * rounds;
-  L.hot_min_chunks = (hot_nnz + chunk_nz - 1) / chunk_nz;
-  if (L.hot_min_chunks < 4) L.hot_min_chunks = 4;
-  L.hot = hot_env != 0 && HotPathShape(embed_width, dtype) &&
-          L.num_chunks >= 2 * L.hot_min_chunks;
-  L.hot_cap = 0;
-  L.hot_ctr_off = L.hot_units_off = L.state_off = L.hot_partial_off = off;
-  if (L.hot) {
-    L.hot_cap = L.num_chunks / L.hot_min_chunks + 1;
-    L.hot_ctr_off = off;
-    off += 256;
-    L.hot_units_off = off;
-    off += AlignUp(static_cast<size_t>(L.hot_cap) * sizeof(int2), 256);
-    L.state_off = off;
-    off += AlignUp(static_cast<size_t>(L.num_chunks), 256);
-    L.hot_partial_off = off;
-    off += AlignUp(static_cast<size_t>(L.hot_cap) * kHotMaxRanges * embed_width *
-                       sizeof(float),
-                   256);
-  }
   L.total = off > 0 ? off : 256;
   return L;
 }
 
-template <typename T, typename IdxT, bool WEIGHTED, int NV>
-void LaunchHot(const BwdArgs& a, cudaStream_t stream) {
-  constexpr int NE = 4 * Elem<T>::kPerWord;
-  constexpr int RPW = (NV * NE >= 32) ? 2 : 4;
-  constexpr int kRpc = kHotWarps * RPW;
-  auto kernel = BwdHotKernel<T, IdxT, WEIGHTED, NV, RPW>;
-  static bool configured = false;  // benign race: same value from every thread
-  if (!configured) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kHotSmemBytes);
-    configured = true;
-  }
-  const int warp_ctas = (a.num_chunks + kWarpsPerCta - 1) / kWarpsPerCta;
-  BwdHotScanAKernel<IdxT><<<warp_ctas, kCtaThreads, 0, stream>>>(a);
-  BwdHotScanBKernel<IdxT><<<warp_ctas, kCtaThreads, 0, stream>>>(a);
-  const int max_groups = (a.hot_cap + kRpc - 1) / kRpc;
-  kernel<<<dim3(kHotMaxRanges, max_groups), kHotThreads, kHotSmemBytes,
-           stream>>>(a);
-  const int wtiles = (a.width + kCtaThreads - 1) / kCtaThreads;
-  BwdHotCombineKernel<<<dim3(a.hot_cap, wtiles), kCtaThreads, 0, stream>>>(
-      a, kRpc);
-  CountLaunch(4);
-}
-
 template <typename T, int V, typename IdxT, bool WEIGHTED>
 void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
-  if constexpr (V == 16) {
-    if (a.chunk_state != nullptr) {
-      if (a.nvec <= 32)
-        LaunchHot<T, IdxT, WEIGHTED, 1>(a, stream);
-      else if (a.nvec <= 64)
-        LaunchHot<T, IdxT, WEIGHTED, 2>(a, stream);
-      else
-        LaunchHot<T, IdxT, WEIGHTED, 4>(a, stream);
-    }
-  }
   dim3 grid(a.num_ctas, col_tiles);
+  if (a.warp_path && a.through_split) {
+    BwdThroughKernel<T, V, IdxT, WEIGHTED><<<grid, kBwdThreads, 0, stream>>>(a);
+    CountLaunch();
+  }
   if (a.warp_path && a.opt_kind == CUEMBED_OPT_SGD)
     BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_SGD>
         <<<grid, kBwdThreads, 0, stream>>>(a);
@@ -856,25 +762,6 @@ void LaunchSegReduceVec(const BwdArgs& a, int vec_bytes, int idx_type,
 }
 
 }  // namespace
-
-int SetBackwardHotPath(int enable) {
-  const int before = BackwardHotPathEnabled();
-  g_hot_path.store(enable != 0 ? 1 : 0);
-  return before;
-}
-
-int BackwardHotCounterOffset(int dtype, int embed_width, int nnz, int idx_type,
-                             size_t* offset) {
-  if (offset == nullptr || nnz < 0 || embed_width <= 0)
-    return CUEMBED_ERR_ARGUMENT;
-  if (dtype < 0 || dtype > 2 || idx_type < 0 || idx_type > 1)
-    return CUEMBED_ERR_DTYPE;
-  RowShape shape;
-  if (!MakeRowShape(embed_width, dtype, &shape)) return CUEMBED_ERR_ROW_BYTES;
-  const BwdLayout L = MakeBwdLayout(nnz, embed_width, shape.lanes, dtype);
-  *offset = L.hot ? L.hot_ctr_off : static_cast<size_t>(-1);
-  return CUEMBED_OK;
-}
 
 namespace {
 struct OptParams {
@@ -958,8 +845,9 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   // column tiles) take the warp-uniform walker (backward_warp.cuh).
   static const int warp_env = EnvInt("CUEMBED_BWD_WARP", 1);
   const int warp_vec =
-      warp_env == 0 ? 0
-                    : (row_bytes == 128 ? 4
+      (warp_env == 0 || opt.kind == CUEMBED_OPT_ADAGRAD)
+          ? 0
+          : (row_bytes == 128 ? 4
                                         : (row_bytes == 256
                                                ? 8
                                                : (row_bytes % 512 == 0 ? 16 : 0)));
@@ -1000,8 +888,7 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   // warp path: its vector width must be allowed by the pointers (otherwise the
   // generic kernel runs with narrower vectors, i.e. 32 lanes as well, so the
   // layout sized above still fits)
-  const bool warp_path = warp_vec != 0 && (bits % warp_vec) == 0 &&
-                         opt.kind != CUEMBED_OPT_ADAGRAD;
+  const bool warp_path = warp_vec != 0 && (bits % warp_vec) == 0;
   if (warp_path) v = warp_vec;
 
   BwdArgs a;
@@ -1032,25 +919,17 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   a.num_ctas = L.num_ctas;
   a.num_chunks = L.num_ctas * (kBwdThreads / a.lanes);
   a.warp_path = warp_path ? 1 : 0;
+  static const int own_env = EnvInt("CUEMBED_BWD_OWN", 1);
+  a.own = own_env != 0 ? 1 : 0;
+  static const int through_env = EnvInt("CUEMBED_BWD_THROUGH", 1);
+  // the lean kernel assumes K is a multiple of 32 (it is: K = 32 * rounds)
+  a.through_split = (warp_path && through_env != 0 && nnz >= 64 * 1024) ? 1 : 0;
   a.opt_kind = opt.kind;
   a.opt_lr = opt.lr;
   a.opt_eps = opt.eps;
   a.opt_state = opt.state;
   a.chunk_nz = a.lanes * a.rounds;
   a.sm_slots = GetDeviceInfo().sm_count;
-  a.hot_min_chunks = L.hot_min_chunks;
-  a.hot_cap = L.hot_cap;
-  a.hot_ctr = reinterpret_cast<int*>(work + L.hot_ctr_off);
-  a.hot_units = reinterpret_cast<int2*>(work + L.hot_units_off);
-  a.hot_partial = reinterpret_cast<float*>(work + L.hot_partial_off);
-  // the layout was sized for the aligned row shape: a call whose pointers only
-  // allow narrower vectors (different chunking) takes the plain path
-  a.chunk_state = (L.hot && v == 16 && a.lanes == shape.lanes)
-                      ? reinterpret_cast<unsigned char*>(work + L.state_off)
-                      : nullptr;
-  // introspection must not read stale counters when the path is skipped
-  if (L.hot && a.chunk_state == nullptr)
-    cudaMemsetAsync(a.hot_ctr, 0, 2 * sizeof(int), stream);
   const int col_tiles = (a.nvec + a.lanes - 1) / a.lanes;
   const bool weighted = transpose_weights != nullptr;
 

@@ -12,8 +12,10 @@
 //   * the row address is ONE IMAD.WIDE (sample id x row pitch + a base pointer
 //     that already contains the lane's column offset and is kept opaque to the
 //     compiler, which otherwise re-adds the kernel-parameter base per load);
-//   * the batches of a round are fully unrolled, so every shuffle has an
-//     immediate source lane;
+//   * the per-lane index words of a round rotate by one batch per iteration,
+//     so every shuffle has an immediate source lane although the batch loop
+//     is not unrolled (a fully unrolled round was 64 KB of code and stalled on
+//     instruction fetch: ncu "no_instruction" 4.0 warps per issue);
 //   * run ends come from a shuffle of the keys (no second key load per lane);
 //   * inverse_mapping is written by the lanes that own a run end, once per
 //     round of 32 nonzeros, instead of two shuffles + a store per run end;
@@ -31,7 +33,9 @@ namespace cuembed_b200 {
 #ifndef BWD_WARP_MINB
 #define BWD_WARP_MINB 6
 #endif
-
+#ifndef BWD_WARP_UNROLL
+#define BWD_WARP_UNROLL 8
+#endif
 // round_T(0.f + float(x)) for every 16-bit element of a vector: x itself except
 // that -0 becomes +0 (what a sum that starts at +0 gives).
 template <typename T, int V>
@@ -74,6 +78,18 @@ __device__ __forceinline__ float ShflWeight(T w, int src) {
   }
 }
 
+template <typename T>
+__device__ __forceinline__ T ShflRaw(T w, int src) {
+  if constexpr (sizeof(T) == 4) {
+    return __shfl_sync(0xffffffffu, w, src);
+  } else {
+    const unsigned short b = *reinterpret_cast<const unsigned short*>(&w);
+    const unsigned short rs = static_cast<unsigned short>(
+        __shfl_sync(0xffffffffu, static_cast<unsigned>(b), src));
+    return *reinterpret_cast<const T*>(&rs);
+  }
+}
+
 // FUSED_OPT: CUEMBED_OPT_NONE or CUEMBED_OPT_SGD (Adagrad stays on the generic
 // kernel: it needs the old table rows in flight).
 template <typename T, int V, typename IdxT, bool WEIGHTED, int FUSED_OPT>
@@ -83,7 +99,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
   constexpr int NW = V / 4;
   constexpr int NE = NW * Elem<T>::kPerWord;
   constexpr unsigned kFull = 0xffffffffu;
-  constexpr int UNROLL = 8;
+  constexpr int UNROLL = BWD_WARP_UNROLL;
   constexpr bool kCopySingles =
       !WEIGHTED && FUSED_OPT == CUEMBED_OPT_NONE && sizeof(T) == 2;
 
@@ -93,17 +109,20 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
   const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
   const IdxT* __restrict__ tidx = static_cast<const IdxT*>(a.tidx);
-  const uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  asm volatile("" : "+r"(row_bytes));  // a plain 32-bit register: RowAddr is one IMAD.WIDE
 
   const int K = a.chunk_nz;
   const int64_t c0 = static_cast<int64_t>(chunk) * K;
   int n = 0;
   if (c0 < a.nnz) n = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
-  // A chunk of a hot unit is summed by the hot-row kernels: nothing to walk
-  // here, it only reports itself as a "through" chunk.
-  const bool hot_chunk =
-      a.chunk_state != nullptr && a.chunk_state[chunk] == kChunkHot;
-  if (hot_chunk) n = 0;
+
+  // Chunks that lie entirely inside one run that began earlier ("through"
+  // chunks: the interiors of hot rows, ~45 % of all chunks at the headline
+  // workload) are summed by BwdThroughKernel when a.through_split is set.
+  if (a.through_split && n == K && c0 > 0 &&
+      __ldg(keys + c0 - 1) == __ldg(keys + c0 + K - 1))
+    return;
 
   const int v = blockIdx.y * 32 + lane;
   const bool active = v < a.nvec;
@@ -126,6 +145,20 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
     if (c0 > 0) cont = __ldg(keys + c0 - 1) == __ldg(keys + c0);
     if (c0 + n < a.nnz)
       last_is_end = __ldg(keys + c0 + n) != __ldg(keys + c0 + n - 1);
+  }
+  // Run ownership across chunk edges (a.own): a run that STARTS inside chunk c
+  // and ends within the first kOwnWindow - 1 elements of chunk c + 1 is finished
+  // by chunk c (it reads those few elements itself) and skipped by chunk c + 1.
+  // Both sides evaluate the same rule from the keys alone, so no flag travels
+  // between them; most two-element chains of the fix-up (~12 000 at the
+  // headline workload) disappear.
+  constexpr int kOwnWindow = 32;
+  bool skip_head = false;
+  if (a.own && cont && n >= kOwnWindow) {
+    const bool short_head = __ldg(keys + c0 + kOwnWindow - 1) != __ldg(keys + c0);
+    const bool prev_inside =
+        c0 - K - 1 < 0 || __ldg(keys + c0 - K - 1) != __ldg(keys + c0 - 1);
+    skip_head = short_head && prev_inside;
   }
   bool in_first = true;
   bool open = false;
@@ -194,21 +227,45 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
     IdxT tk = 0;
     if (write_inv) tk = __ldg(tidx + c0 + p);
 
-#pragma unroll
-    for (int jb = 0; jb < 32; jb += UNROLL) {
-      if (jb >= cnt) break;  // warp-uniform
+    // The batch loop is NOT unrolled (a fully unrolled round was 64 KB of code
+    // and stalled on instruction fetch); instead the per-lane words rotate by
+    // one batch per iteration, so the shuffles still use immediate lanes 0..7.
+    IdxT sid_r = sid, key_r = key;
+    T w_r = w;
+    unsigned ends = endsw;
+    int rem0 = cnt;
+    if (skip_head) {
+      // the previous chunk finishes our head run: start behind it
+      const IdxT k0 = ShflIdx<IdxT>(key, 0, 32);
+      const unsigned same = __ballot_sync(kFull, key == k0 && p < n);
+      const int e = __ffs(~same) - 1;  // 1 .. kOwnWindow - 1
+      const int from = (lane + e) & 31;
+      sid_r = ShflIdx<IdxT>(sid_r, from, 32);
+      key_r = ShflIdx<IdxT>(key_r, from, 32);
+      if constexpr (WEIGHTED) w_r = ShflRaw<T>(w_r, from);
+      ends >>= e;
+      rem0 -= e;
+      skip_head = false;
+      cont = false;
+    }
+#pragma unroll 1
+    for (int rem = rem0; rem > 0; rem -= UNROLL) {
+      // UNROLL independent row loads issued before the first add.  Lanes past
+      // the end of the chunk carry sample id 0: a valid, harmless load that is
+      // never accumulated.
       VecT vals[UNROLL];
-      float wf[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        // lanes past the end of the chunk carry sample id 0: a valid,
-        // harmless load that is never accumulated
-        const IdxT s = ShflIdx<IdxT>(sid, jb + u, 32);
-        if constexpr (WEIGHTED) wf[u] = ShflWeight<T>(w, jb + u);
-        vals[u] = LdgVec<V>(RowAddr<IdxT>(gy, s, row_bytes));
+      for (int u = 0; u < UNROLL; ++u)
+        vals[u] = LdgVec<V>(
+            RowAddr<IdxT>(gy, ShflIdx<IdxT>(sid_r, u, 32), row_bytes));
+      const int from = (lane + UNROLL) & 31;
+      float wf[UNROLL];
+      if constexpr (WEIGHTED) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) wf[u] = ShflWeight<T>(w_r, u);
       }
-      const unsigned m8 = (endsw >> jb) & ((1u << UNROLL) - 1u);
-      if (m8 == 0u && jb + UNROLL <= cnt) {
+      const unsigned m8 = ends & ((1u << UNROLL) - 1u);
+      if (m8 == 0u && rem >= UNROLL) {
         // no run ends in this batch (the interior of a long run)
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -218,31 +275,39 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
             AccumulateVec<T, V>(vals[u], acc);
         }
         open = true;
-        continue;
-      }
+      } else {
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int j = jb + u;
-        if (j >= cnt) break;  // warp-uniform
-        const bool is_end = ((m8 >> u) & 1u) != 0u;
-        if constexpr (kCopySingles) {
-          if (is_end && !open && !(in_first && cont)) {
-            // a run of length one: round(0 + x) == x (-0 -> +0): row copy
-            const IdxT krow = ShflIdx<IdxT>(key, j, 32);
-            if (active)
-              StcsVec<V>(RowAddr<IdxT>(out, krow, row_bytes),
-                         ZeroPlus<T, V>(vals[u]));
-            in_first = false;
-            continue;
+        for (int u = 0; u < UNROLL; ++u) {
+          if (u < rem) {  // warp-uniform
+            const bool is_end = ((m8 >> u) & 1u) != 0u;
+            bool copied = false;
+            if constexpr (kCopySingles) {
+              if (is_end && !open && !(in_first && cont)) {
+                // a run of length one: round(0 + x) == x (-0 -> +0): row copy
+                const IdxT krow = ShflIdx<IdxT>(key_r, u, 32);
+                if (active)
+                  StcsVec<V>(RowAddr<IdxT>(out, krow, row_bytes),
+                             ZeroPlus<T, V>(vals[u]));
+                in_first = false;
+                copied = true;
+              }
+            }
+            if (!copied) {
+              if constexpr (WEIGHTED)
+                AccumulateVecWeighted<T, V>(vals[u], wf[u], acc);
+              else
+                AccumulateVec<T, V>(vals[u], acc);
+              open = true;
+              if (is_end) flush(ShflIdx<IdxT>(key_r, u, 32));
+            }
           }
         }
-        if constexpr (WEIGHTED)
-          AccumulateVecWeighted<T, V>(vals[u], wf[u], acc);
-        else
-          AccumulateVec<T, V>(vals[u], acc);
-        open = true;
-        if (is_end) flush(ShflIdx<IdxT>(key, j, 32));
       }
+      // next batch: rotate by UNROLL lanes
+      ends >>= UNROLL;
+      sid_r = ShflIdx<IdxT>(sid_r, from, 32);
+      key_r = ShflIdx<IdxT>(key_r, from, 32);
+      if constexpr (WEIGHTED) w_r = ShflRaw<T>(w_r, from);
     }
     if (write_inv) static_cast<IdxT*>(a.inverse_mapping)[key] = tk;
   }
@@ -255,12 +320,52 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
       head_kind = kHeadThrough;
       if (active) StorePartial<NE>(my_head + v * NE, acc);
     } else {
-      has_tail = 1;
-      tail_row = __ldg(keys + c0 + n - 1);
-      if (active) StorePartial<NE>(my_tail + v * NE, acc);
+      // the run started in this chunk and continues into the next one
+      bool extended = false;
+      const int64_t nx = c0 + K;
+      if (a.own && a.nnz - nx >= kOwnWindow) {
+        const IdxT tkey = __ldg(keys + nx - 1);
+        if (__ldg(keys + nx + kOwnWindow - 1) != tkey) {
+          // ... and ends within the next kOwnWindow - 1 elements: finish it here
+          const IdxT key_x = __ldg(keys + nx + lane);
+          IdxT sid_x = __ldg(sids + nx + lane);
+          T w_x = T();
+          if constexpr (WEIGHTED) w_x = __ldg(weights + nx + lane);
+          const unsigned same = __ballot_sync(kFull, key_x == tkey);
+          const int e = __ffs(~same) - 1;  // 1 .. kOwnWindow - 1
+#pragma unroll 1
+          for (int rem = e; rem > 0; rem -= UNROLL) {
+            VecT vals[UNROLL];
+            float wf[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              const IdxT sx = ShflIdx<IdxT>(sid_x, u, 32);
+              if constexpr (WEIGHTED) wf[u] = ShflWeight<T>(w_x, u);
+              vals[u] = LdgVec<V>(RowAddr<IdxT>(gy, sx, row_bytes));
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              if (u >= rem) break;  // warp-uniform
+              if constexpr (WEIGHTED)
+                AccumulateVecWeighted<T, V>(vals[u], wf[u], acc);
+              else
+                AccumulateVec<T, V>(vals[u], acc);
+            }
+            const int from = (lane + UNROLL) & 31;
+            sid_x = ShflIdx<IdxT>(sid_x, from, 32);
+            if constexpr (WEIGHTED) w_x = ShflRaw<T>(w_x, from);
+          }
+          flush(tkey);
+          extended = true;
+        }
+      }
+      if (!extended) {
+        has_tail = 1;
+        tail_row = __ldg(keys + c0 + n - 1);
+        if (active) StorePartial<NE>(my_tail + v * NE, acc);
+      }
     }
   }
-  if (hot_chunk) head_kind = kHeadThrough;
   if (lane == 0 && blockIdx.y == 0) {
     a.meta[chunk * 2 + 0] = head_kind;
     a.meta[chunk * 2 + 1] = has_tail;
@@ -268,6 +373,83 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
     a.meta_row[chunk * 2 + 1] = static_cast<long long>(tail_row);
     // work list of the fix-up (any order: every chain is summed on its own)
     if (has_tail) a.tail_list[1 + atomicAdd(a.tail_list, 1)] = chunk;
+  }
+}
+
+// A "through" chunk (all K nonzeros belong to one run that began in an earlier
+// chunk) is a plain sum of K grad_y rows into the chunk's fp32 head partial: no
+// run ends, no stores to the gradient, no inverse mapping.  Without that
+// bookkeeping the loop needs ~50 registers instead of 80, so 8 instead of 6
+// CTAs are resident per SM and the row gathers run close to the measured L2
+// gather ceiling; the general walker skips these chunks.  Same association
+// order as the walker (sequential inside the chunk), so results are identical.
+template <typename T, int V, typename IdxT, bool WEIGHTED>
+__global__ void __launch_bounds__(kBwdThreads, 8)
+    BwdThroughKernel(const BwdArgs a) {
+  using VecT = typename VecBits<V>::type;
+  constexpr int NW = V / 4;
+  constexpr int NE = NW * Elem<T>::kPerWord;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int UNROLL = 8;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
+  const IdxT* __restrict__ keys = static_cast<const IdxT*>(a.keys);
+  const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
+  const T* __restrict__ weights = static_cast<const T*>(a.weights);
+  const int K = a.chunk_nz;
+  const int64_t c0 = static_cast<int64_t>(chunk) * K;
+  if (c0 == 0 || c0 + K > a.nnz) return;
+  if (__ldg(keys + c0 - 1) != __ldg(keys + c0 + K - 1)) return;
+
+  uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  asm volatile("" : "+r"(row_bytes));
+  const int v = blockIdx.y * 32 + lane;
+  const bool active = v < a.nvec;
+  const char* gy = static_cast<const char*>(a.grad_y) +
+                   static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  asm volatile("" : "+l"(gy));
+
+  float acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+  IdxT sid_n = __ldg(sids + c0 + lane);
+  T w_n = T();
+  if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + lane);
+#pragma unroll 1
+  for (int r = 0; r * 32 < K; ++r) {
+    IdxT sid_r = sid_n;
+    T w_r = w_n;
+    if ((r + 1) * 32 < K) {
+      sid_n = __ldg(sids + c0 + (r + 1) * 32 + lane);
+      if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + (r + 1) * 32 + lane);
+    }
+    const int from = (lane + UNROLL) & 31;
+#pragma unroll 1
+    for (int jb = 0; jb < 32; jb += UNROLL) {
+      VecT vals[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        vals[u] = LdgVec<V>(
+            RowAddr<IdxT>(gy, ShflIdx<IdxT>(sid_r, u, 32), row_bytes));
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if constexpr (WEIGHTED)
+          AccumulateVecWeighted<T, V>(vals[u], ShflWeight<T>(w_r, u), acc);
+        else
+          AccumulateVec<T, V>(vals[u], acc);
+      }
+      sid_r = ShflIdx<IdxT>(sid_r, from, 32);
+      if constexpr (WEIGHTED) w_r = ShflRaw<T>(w_r, from);
+    }
+  }
+  if (active)
+    StorePartial<NE>(
+        a.scratch + (static_cast<size_t>(chunk) * 2 + 0) * a.width + v * NE, acc);
+  if (lane == 0 && blockIdx.y == 0) {
+    a.meta[chunk * 2 + 0] = kHeadThrough;
+    a.meta[chunk * 2 + 1] = 0;
+    a.meta_row[chunk * 2 + 0] = 0;
+    a.meta_row[chunk * 2 + 1] = 0;
   }
 }
 

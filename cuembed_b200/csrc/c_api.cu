@@ -148,15 +148,6 @@ int cuembed_backward_update(const void* grad_y, int dtype, int embed_width,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
-int cuembed_set_backward_hot_path(int enable) {
-  return SetBackwardHotPath(enable);
-}
-
-int cuembed_backward_ws_hot_offset(int dtype, int embed_width, int nnz,
-                                   int idx_type, size_t* offset) {
-  return BackwardHotCounterOffset(dtype, embed_width, nnz, idx_type, offset);
-}
-
 // Scratch for the drop-in signature (no workspace argument): a library-owned
 // stream-ordered pool per device that keeps its memory between calls, so the
 // steady state costs no driver allocation.  cudaMallocFromPoolAsync /

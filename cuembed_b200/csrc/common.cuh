@@ -361,23 +361,20 @@ __device__ __forceinline__ void StoreFloatsAs(void* out_row, int64_t elem_off,
 }
 
 // Address of row `row` of a row-major array: base + row * pitch.  Indices are
-// non-negative; with 32-bit indices this is exactly ONE instruction
-// (IMAD.WIDE.U32 with the 64-bit base as addend) -- written in PTX because the
-// compiler otherwise splits it into a wide multiply plus two adds.  `base`
-// should already contain the lane's column offset.
+// non-negative; with 32-bit indices and a 32-bit pitch this compiles to exactly
+// ONE instruction (IMAD.WIDE.U32 with the 64-bit base as addend) PROVIDED that
+// `base` is an opaque register pair (asm volatile("" : "+l"(base)) after the
+// lane's column offset has been added) -- otherwise the compiler re-adds the
+// kernel-parameter base with two more adds per row.  (An explicit PTX
+// mad.wide.u32 is split by ptxas into a multiply and two adds; the plain C++
+// expression is not.)
 template <typename IdxT>
 __device__ __forceinline__ const char* RowAddr(const char* base, IdxT row,
                                                uint32_t pitch) {
-  if constexpr (sizeof(IdxT) == 4) {
-    uint64_t r;
-    asm("mad.wide.u32 %0, %1, %2, %3;"
-        : "=l"(r)
-        : "r"(static_cast<uint32_t>(row)), "r"(pitch),
-          "l"(reinterpret_cast<uint64_t>(base)));
-    return reinterpret_cast<const char*>(r);
-  } else {
+  if constexpr (sizeof(IdxT) == 4)
+    return base + static_cast<uint64_t>(static_cast<uint32_t>(row)) * pitch;
+  else
     return base + static_cast<uint64_t>(row) * pitch;
-  }
 }
 template <typename IdxT>
 __device__ __forceinline__ char* RowAddr(char* base, IdxT row, uint32_t pitch) {

@@ -188,7 +188,8 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
   asm volatile("" : "+l"(params));
   const IdxT* __restrict__ indices = static_cast<const IdxT*>(a.indices);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
-  const uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  asm volatile("" : "+r"(row_bytes));  // a plain 32-bit register: RowAddr is one IMAD.WIDE
   // All 32 lanes of a warp run the loops below in lockstep (bounds are
   // warp-wide maxima) so every shuffle uses the constant full mask; lane
   // groups with shorter bags idle through predicates.
@@ -232,6 +233,13 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
 #pragma unroll 1
     for (int j0 = 0; j0 < len_max; j0 += G) {
       const int cnt = min(G, len - j0);  // may be <= 0 for a finished group
+      // The index (and weight) words rotate by one batch per iteration inside
+      // the lane group, so every broadcast shuffle has an immediate source lane
+      // (G >= UNROLL or G == 8 == UNROLL: rotating by UNROLL stays inside the
+      // group).
+      IdxT idx_rot = idx_cur;
+      T w_rot = w_cur;
+      const int rot_from = (lane_g + UNROLL) & (G - 1);
 #pragma unroll 1
       for (int jb = 0; jb < G && j0 + jb < len_max; jb += UNROLL) {
         VecT vals[UNROLL];
@@ -239,10 +247,12 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
         // UNROLL independent row loads issued before the first accumulate.
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const IdxT row = ShflIndex<IdxT>(kFull, idx_cur, jb + u, G);
-          if constexpr (WEIGHTED) wv[u] = ShflElem<T>(kFull, w_cur, jb + u, G);
+          const IdxT row = ShflIndex<IdxT>(kFull, idx_rot, u, G);
+          if constexpr (WEIGHTED) wv[u] = ShflElem<T>(kFull, w_rot, u, G);
           vals[u] = LdgVec<V>(RowAddr<IdxT>(params, row, row_bytes));
         }
+        idx_rot = ShflIndex<IdxT>(kFull, idx_rot, rot_from, G);
+        if constexpr (WEIGHTED) w_rot = ShflElem<T>(kFull, w_rot, rot_from, G);
         if (__all_sync(kFull, jb + UNROLL <= cnt)) {
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u) {

@@ -60,10 +60,6 @@ int LaunchBackwardUpdate(const void* grad_y, int dtype, int embed_width, int nnz
                          float eps, void* params, float* state, char* work,
                          size_t* lwork, cudaStream_t stream);
 
-int SetBackwardHotPath(int enable);
-int BackwardHotCounterOffset(int dtype, int embed_width, int nnz, int idx_type,
-                             size_t* offset);
-
 int LaunchShardSelect(const void* indices, int idx_type, const void* offsets,
                       int off_type, const void* weights, int weight_dtype,
                       int batch_size, int num_hots, long long row_lo,

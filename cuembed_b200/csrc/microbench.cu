@@ -18,13 +18,12 @@
 
 namespace cuembed_b200 {
 
-template <int G, bool NO_L1>
-__global__ void __launch_bounds__(kCtaThreads, 4)
+template <int G, bool NO_L1, int UNROLL = 8>
+__global__ void __launch_bounds__(kCtaThreads, (UNROLL <= 8 ? 4 : 2))
     GatherRowsKernel(const char* __restrict__ buf, uint32_t row_bytes,
                      const int* __restrict__ rows, long long n,
                      unsigned* __restrict__ sink) {
   constexpr unsigned kFull = 0xffffffffu;
-  constexpr int UNROLL = 8;
   const int lane = threadIdx.x & 31;
   const int lane_g = lane & (G - 1);
   const int gw = lane / G;                     // lane group within the warp
@@ -59,9 +58,138 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
   if (acc == 0x9e3779b9u) sink[0] = acc;  // keeps the loads alive
 }
 
+// ---- the same gather with the rows landing in SHARED MEMORY through the bulk
+// copy engine (cp.async.bulk, SASS UBLKCP) instead of registers: every lane
+// issues ONE 512-byte row copy for its own index (one warp instruction starts
+// up to 32 row copies), completion is counted on an mbarrier per stage, and
+// the lanes then read the rows from shared memory (LDS.128).  Rows in flight
+// are bounded by shared memory (S stages x R rows x 512 B per warp), not by
+// registers.
+__device__ __forceinline__ uint32_t MbSmemAddr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+template <int R, int S, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+    GatherRowsBulkKernel(const char* __restrict__ buf,
+                         const int* __restrict__ rows, long long n,
+                         unsigned* __restrict__ sink) {
+  constexpr int kRow = 512;
+  extern __shared__ __align__(128) unsigned char mb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* wbuf = mb_smem + static_cast<size_t>(warp) * S * R * kRow;
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(mb_smem + static_cast<size_t>(W) * S * R * kRow) +
+      warp * S;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                       MbSmemAddr(bars + s)),
+                   "r"(1)
+                   : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long gw = static_cast<long long>(blockIdx.x) * W + warp;
+  const long long nw = static_cast<long long>(gridDim.x) * W;
+  const long long n_batches = (n + R - 1) / R;
+  auto issue = [&](long long k, int stage) {
+    const long long base = k * R;
+    const int cnt = static_cast<int>(min(static_cast<long long>(R), n - base));
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                       MbSmemAddr(bars + stage)),
+                   "r"(cnt * kRow)
+                   : "memory");
+    __syncwarp();
+    if (lane < cnt) {
+      const int r = __ldg(rows + base + lane);
+      const char* src = buf + static_cast<uint64_t>(static_cast<uint32_t>(r)) * kRow;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+          "[%0], [%1], %2, [%3];" ::"r"(MbSmemAddr(wbuf + (stage * R + lane) * kRow)),
+          "l"(src), "r"(kRow), "r"(MbSmemAddr(bars + stage))
+          : "memory");
+    }
+  };
+  // batches of this warp: gw, gw + nw, ...
+  long long k_issue = gw;
+  for (int s = 0; s < S && k_issue < n_batches; ++s, k_issue += nw) issue(k_issue, s);
+  uint32_t acc = 0;
+  int it = 0;
+  for (long long k = gw; k < n_batches; k += nw, ++it) {
+    const int stage = it % S;
+    const uint32_t parity = (it / S) & 1;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(MbSmemAddr(bars + stage)),
+        "r"(parity)
+        : "memory");
+    const unsigned char* st = wbuf + static_cast<size_t>(stage) * R * kRow + lane * 16;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint4 v = *reinterpret_cast<const uint4*>(st + j * kRow);
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    __syncwarp();  // every lane has its data in registers: the stage is free
+    if (k_issue < n_batches) {
+      issue(k_issue, stage);
+      k_issue += nw;
+    }
+  }
+  if (acc == 0x9e3779b9u) sink[0] = acc;
+}
+
+template <int R, int S, int W>
+int LaunchGatherBulk(const char* buf, const int* rows, long long n,
+                     unsigned* sink, cudaStream_t stream) {
+  auto k = GatherRowsBulkKernel<R, S, W>;
+  const size_t smem = static_cast<size_t>(W) * S * R * 512 + W * S * 8 + 128;
+  static PerDeviceInt configured;
+  if (configured.Get() == 0) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return CUEMBED_ERR_CUDA;
+    configured.Set(1);
+  }
+  k<<<GetDeviceInfo().sm_count, W * 32, smem, stream>>>(buf, rows, n, sink);
+  CountLaunch();
+  return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+}
+
 }  // namespace cuembed_b200
 
 using namespace cuembed_b200;  // NOLINT
+
+// variant: 0 = 32 rows x 2 stages x 6 warps, 1 = 16 x 3 x 8, 2 = 32 x 1 x 12,
+// 3 = 16 x 2 x 12, 4 = 8 x 4 x 12  (rows per stage x stages x warps per SM)
+extern "C" int cuembed_microbench_gather_bulk(const void* buf, int row_bytes,
+                                              const int* rows, long long n,
+                                              int variant, unsigned* sink,
+                                              cuembed_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (buf == nullptr || rows == nullptr || sink == nullptr || n < 0)
+    return CUEMBED_ERR_ARGUMENT;
+  if (row_bytes != 512) return CUEMBED_ERR_ROW_BYTES;
+  if ((reinterpret_cast<uintptr_t>(buf) & 15) != 0) return CUEMBED_ERR_ARGUMENT;
+  const char* b = static_cast<const char*>(buf);
+  switch (variant) {
+    case 0: return LaunchGatherBulk<32, 2, 6>(b, rows, n, sink, stream);
+    case 1: return LaunchGatherBulk<16, 3, 8>(b, rows, n, sink, stream);
+    case 2: return LaunchGatherBulk<32, 1, 12>(b, rows, n, sink, stream);
+    case 3: return LaunchGatherBulk<16, 2, 12>(b, rows, n, sink, stream);
+    case 4: return LaunchGatherBulk<8, 4, 12>(b, rows, n, sink, stream);
+    default: return CUEMBED_ERR_ARGUMENT;
+  }
+}
 
 extern "C" int cuembed_microbench_gather(const void* buf, int row_bytes,
                                          const int* rows, long long n,
@@ -84,7 +212,11 @@ extern "C" int cuembed_microbench_gather(const void* buf, int row_bytes,
       GatherRowsKernel<GG, false><<<grid, kCtaThreads, 0, stream>>>(            \
           b, static_cast<uint32_t>(row_bytes), rows, n, sink);                  \
   } while (0)
-  if (row_bytes == 512)
+  if (row_bytes == 512 && no_l1_allocate == 2) {
+    // deeper pipeline: 16 rows in flight per warp, 2 CTAs per SM
+    GatherRowsKernel<32, false, 16><<<GetDeviceInfo().sm_count * 2, kCtaThreads, 0, stream>>>(
+        b, static_cast<uint32_t>(row_bytes), rows, n, sink);
+  } else if (row_bytes == 512)
     GATHER(32);
   else if (row_bytes == 256)
     GATHER(16);

@@ -205,26 +205,6 @@ int cuembed_backward_update(const void* grad_y, int dtype, int embed_width,
                             char* work, size_t* lwork, cuembed_stream_t stream);
 
 /*
- * Experimental hot-row path of the backward: the interiors of
- * very long runs are summed sample tile by sample tile through shared memory
- * (TMA bulk loads) instead of one grad_y row gather per nonzero.  Results are
- * the same sums in a different, still fixed, association order.  OFF by default
- * (measured slower end to end on B200); process-wide switch, returns the
- * previous setting.  The workspace size of cuembed_backward_ws depends on it.
- */
-int cuembed_set_backward_hot_path(int enable);
-
-/*
- * Introspection for tests and benchmarks: byte offset, inside the workspace of
- * cuembed_backward_ws for this problem shape, of two int32 counters that the
- * call leaves behind: {number of hot units, largest sample id of a hot unit}
- * (the hot-row path of the backward).  *offset = (size_t)-1 when
- * that path is switched off for the shape.
- */
-int cuembed_backward_ws_hot_offset(int dtype, int embed_width, int nnz,
-                                   int idx_type, size_t* offset);
-
-/*
  * Row-sharded multi-GPU mode (new: the reference is single-GPU, README.md:110).
  * A GPU that owns table rows [row_lo, row_hi) selects, from the replicated
  * lookup indices of the global batch, the lookups that fall into its range:
@@ -375,11 +355,19 @@ int cuembed_shard_allgather_push(const void* src, size_t bytes,
  * row, 16-byte loads, 8 rows in flight, persistent grid) and no arithmetic
  * beyond one XOR per word.  On an L2-resident buffer this is the L2 -> SM
  * gather ceiling, on a multi-GB buffer the DRAM gather ceiling.
- * no_l1_allocate != 0 uses ld.global.nc.L1::no_allocate.  sink: 4 bytes.
+ * no_l1_allocate: 1 = ld.global.nc.L1::no_allocate, 2 = 16 rows in flight per
+ * warp (512-byte rows only).  sink: 4 bytes.
  */
 int cuembed_microbench_gather(const void* buf, int row_bytes, const int* rows,
                               long long n, int no_l1_allocate, unsigned* sink,
                               cuembed_stream_t stream);
+/* The same gather with the rows landing in shared memory through per-lane bulk
+ * copies (cp.async.bulk + mbarrier) and read back with LDS.128; row_bytes must
+ * be 512.  variant selects rows per stage x stages x warps per SM:
+ * 0 = 32x2x6, 1 = 16x3x8, 2 = 32x1x12, 3 = 16x2x12, 4 = 8x4x12. */
+int cuembed_microbench_gather_bulk(const void* buf, int row_bytes,
+                                   const int* rows, long long n, int variant,
+                                   unsigned* sink, cuembed_stream_t stream);
 
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */

@@ -330,49 +330,45 @@ def test_backward_long_runs_and_power_law(cuda_lib, oracle, dt):
     assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, "single run")
 
 
-def _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped):
-    """EmbeddingBackward with explicit workspace; also returns the number of
-    hot units the call found (-1: hot-row path off for the shape)."""
+def _backward_explicit_ws(p, t_idx, t_sid, t_w, remapped):
+    """EmbeddingBackward through the explicit-workspace entry point, output
+    poisoned with NaN first."""
     dt = gh.TORCH_DT[p.dt]
     num_rows = (int(remapped[-1].item()) + 1) if p.compressed else p.num_categories
     grad = torch.full((num_rows, p.width), float("nan"), dtype=dt, device=gh.DEV)
     inv = (torch.full((num_rows,), -1, dtype=t_idx.dtype, device=gh.DEV)
            if p.compressed else None)
-    before = ce.set_backward_hot_path(True)  # experimental path, off by default
-    try:
-        work = torch.empty(ce.backward_workspace_bytes(dt, p.width, p.nnz, t_idx.dtype),
-                           dtype=torch.uint8, device=gh.DEV)
-        ce.EmbeddingBackward(gh.to_dev(p.grad_y), p.width, num_rows, p.nnz, t_idx, t_sid,
-                             remapped, t_w, False, grad, inv, work=work)
-        torch.cuda.synchronize()
-        n_hot = ce.backward_hot_units(work, dt, p.width, p.nnz, t_idx.dtype)
-    finally:
-        ce.set_backward_hot_path(before)
-    return gh.to_host(grad), (inv.cpu().numpy() if inv is not None else None), n_hot
+    work = torch.empty(ce.backward_workspace_bytes(dt, p.width, p.nnz, t_idx.dtype),
+                       dtype=torch.uint8, device=gh.DEV)
+    ce.EmbeddingBackward(gh.to_dev(p.grad_y), p.width, num_rows, p.nnz, t_idx, t_sid,
+                         remapped, t_w, False, grad, inv, work=work)
+    torch.cuda.synchronize()
+    return gh.to_host(grad), (inv.cpu().numpy() if inv is not None else None)
 
 
 HOT_CASES = [
     # width, dtype, weighted, compressed, index type
-    (32, F32, False, True, np.int32),     # 128-byte rows: 4 rows per warp step
-    (128, F16, True, True, np.int32),     # 256-byte rows: 2 rows per warp step
-    (256, F16, False, True, np.int32),    # the headline row shape
+    (32, F32, False, True, np.int32),     # 128-byte rows: warp walker, 4-byte vectors
+    (128, F16, True, True, np.int32),     # 256-byte rows: warp walker, 8-byte vectors
+    (256, F16, False, True, np.int32),    # the headline row shape (row copies for single hits)
     (256, BF16, True, False, np.int64),   # full gradient, 64-bit indices
     (128, F32, True, True, np.int64),     # 512-byte fp32 rows
-    (512, F16, False, True, np.int32),    # 1 KB rows: 2 vectors per lane
-    (512, F32, True, True, np.int32),     # 2 KB rows: 4 vectors per lane
-    (1024, F16, False, False, np.int32),  # 2 KB 16-bit rows: 2 units per warp
-    (48, F16, False, True, np.int32),     # 96-byte rows: 8-byte vectors, path off
-    (96, F16, False, True, np.int32),     # 192-byte rows: 12 of 16 lanes
+    (512, F16, False, True, np.int32),    # 1 KB rows: two column tiles
+    (512, F32, True, True, np.int32),     # 2 KB rows: four column tiles
+    (1024, F16, False, False, np.int32),  # 2 KB 16-bit rows
+    (48, F16, False, True, np.int32),     # 96-byte rows: generic lane-group walker
+    (96, F16, False, True, np.int32),     # 192-byte rows: generic walker, 12 of 16 lanes
 ]
 
 
 @pytest.mark.parametrize("case", HOT_CASES, ids=lambda c: f"w{c[0]}-dt{c[1]}-{'w' if c[2] else 'u'}")
 def test_backward_hot_rows(cuda_lib, oracle, case):
-    """Batches in which a few dozen rows receive thousands of lookups each: the
-    interiors of those runs go through the sample-tile kernel (hot units > 0 is
-    asserted), everything else through the chunk walker.  Integer gradients and
-    power-of-two weights: every partial sum is exact in fp32, so the result
-    must equal the fp32-accumulating oracle whatever the association."""
+    """Batches in which a few dozen rows receive thousands of lookups each (runs
+    that span dozens of chunks: head / through / tail partials, both fix-up
+    levels) next to hundreds of rows hit once, for every row shape of the two
+    chunk walkers.  Integer gradients and power-of-two weights: every partial
+    sum is exact in fp32, so the result must equal the fp32-accumulating oracle
+    whatever the association."""
     width, dt, weighted, compressed, it = case
     p = Problem(12288, width, 12, "sum", weighted=weighted, compressed=compressed, dt=dt,
                 num_categories=2500, alpha=1.15, seed=41, index_dtype=it)
@@ -380,18 +376,14 @@ def test_backward_hot_rows(cuda_lib, oracle, case):
     c = p.cpu_transpose(oracle)
     assert np.array_equal(t_sid.cpu().numpy(), c[2])
     (c_grad, c_inv), _ = p.cpu_backward(oracle, *c[1:], acc_f32=True)
-    g_grad, g_inv, n_hot = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
-    if width * (4 if dt == F32 else 2) < 128:
-        assert n_hot == -1, "rows of fewer than 8 x 16 bytes stay on the chunk walker"
-    else:
-        assert n_hot > 0, "the hot-row path did not engage"
+    g_grad, g_inv = _backward_explicit_ws(p, t_idx, t_sid, t_w, remapped)
     touched = np.zeros(c_grad.shape[0], bool)
     touched[c[4] if compressed else c[1]] = True
     assert value_equal(raw_rows(g_grad, touched), raw_rows(c_grad, touched)), \
-        _diff(raw_rows(g_grad, touched), raw_rows(c_grad, touched), f"hot backward n_hot={n_hot}")
+        _diff(raw_rows(g_grad, touched), raw_rows(c_grad, touched), "hot rows")
     if compressed:
         assert np.array_equal(g_inv, c_inv)
-    # the default path (chunk walker only) gives the same values
+    # the drop-in entry point (library-owned scratch) gives the same values
     g2, _, _ = gh.gpu_backward(p, t_idx, t_sid, t_w, remapped)
     assert value_equal(g2, g_grad)
 
@@ -403,11 +395,9 @@ def raw_rows(a, mask):
 
 
 def test_backward_hot_rows_unsorted_samples_and_concat(cuda_lib, oracle):
-    """The sample-tile kernel needs ascending sample ids inside a run; a caller
-    may pass them in any order (the reference only asks for grouped indices,
-    cuembed/README.md).  Runs whose sample ids are not ascending, and runs that
-    are too sparse in sample space (concat: sample id = lookup position), must
-    stay on the chunk walker and still give the right sums."""
+    """A caller may pass the sample ids of a run in any order (the reference only
+    asks for grouped indices, cuembed/README.md): runs with descending sample
+    ids, and concat (sample id = lookup position), give the right sums."""
     p = Problem(12288, 64, 12, "sum", weighted=True, compressed=True, dt=F32,
                 num_categories=2500, alpha=1.15, seed=43)
     rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
@@ -420,9 +410,8 @@ def test_backward_hot_rows_unsorted_samples_and_concat(cuda_lib, oracle):
     r_sid = np.ascontiguousarray(c[2][perm])
     r_w = np.ascontiguousarray(c[3][perm])
     (c_grad, c_inv), _ = p.cpu_backward(oracle, c[1], r_sid, r_w, c[4], acc_f32=True)
-    g_grad, g_inv, n_hot = _backward_with_hot_count(
+    g_grad, g_inv = _backward_explicit_ws(
         p, t_idx, gh.to_dev(r_sid), gh.to_dev(r_w), remapped)
-    assert n_hot == 0, "descending sample ids must not be treated as hot units"
     assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, "reversed runs")
     assert np.array_equal(g_inv, c_inv)
     # concat: every lookup is its own "sample"
@@ -431,16 +420,15 @@ def test_backward_hot_rows_unsorted_samples_and_concat(cuda_lib, oracle):
     rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(pc)
     cc = pc.cpu_transpose(oracle)
     (c_grad, c_inv), _ = pc.cpu_backward(oracle, *cc[1:], acc_f32=True)
-    g_grad, g_inv, n_hot = _backward_with_hot_count(pc, t_idx, t_sid, t_w, remapped)
-    assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, f"concat n_hot={n_hot}")
+    g_grad, g_inv = _backward_explicit_ws(pc, t_idx, t_sid, t_w, remapped)
+    assert value_equal(g_grad, c_grad), _diff(g_grad, c_grad, "concat")
     assert np.array_equal(g_inv, c_inv)
 
 
 def test_backward_hot_rows_real_valued_and_deterministic(cuda_lib, oracle):
-    """Real-valued gradients through the hot-row path: within 1e-5 of sum|terms|
-    of the sequential fp32 oracle (north_star tolerance for a different
-    accumulation order), and bit-identical from run to run although hot units
-    are registered in arbitrary order."""
+    """Real-valued gradients with long runs: within 1e-5 of sum|terms| of the
+    sequential fp32 oracle (north_star tolerance for a different accumulation
+    order across chunks), and bit-identical from run to run."""
     rng = np.random.default_rng(45)
     p = Problem(12288, 256, 12, "sum", weighted=True, compressed=True, dt=F32,
                 num_categories=2500, alpha=1.15, seed=46)
@@ -449,15 +437,14 @@ def test_backward_hot_rows_real_valued_and_deterministic(cuda_lib, oracle):
     rows, t_idx, t_sid, t_w, remapped = gh.gpu_transpose(p)
     c = p.cpu_transpose(oracle)
     (c_grad, _), num_rows = p.cpu_backward(oracle, *c[1:])
-    g_grad, _, n_hot = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
-    assert n_hot > 0
+    g_grad, _ = _backward_explicit_ws(p, t_idx, t_sid, t_w, remapped)
     l1 = np.zeros((num_rows, p.width))
     np.add.at(l1, c[4], np.abs(p.grad_y.astype(np.float64)[c[2]] *
                                c[3].astype(np.float64)[:, None]))
     rel = np.abs(g_grad.astype(np.float64) - c_grad) / np.maximum(l1, 1e-30)
     assert np.max(rel) <= 1e-5, float(np.max(rel))
     for _ in range(3):
-        g2, _, _ = _backward_with_hot_count(p, t_idx, t_sid, t_w, remapped)
+        g2, _ = _backward_explicit_ws(p, t_idx, t_sid, t_w, remapped)
         assert bits_equal(g2, g_grad)
 
 
