@@ -65,7 +65,6 @@ struct BwdArgs {
   // the TABLE and every finished row sum an in-place update of its table row
   int warp_path;     // rows that one warp covers: BwdWarpKernel (backward_warp.cuh)
   int own;           // warp path: run ownership across chunk edges
-  int through_split; // warp path: through chunks go to BwdThroughKernel
   int opt_kind;      // CUEMBED_OPT_NONE / SGD / ADAGRAD
   float opt_lr;
   float opt_eps;
@@ -705,10 +704,6 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
 template <typename T, int V, typename IdxT, bool WEIGHTED>
 void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   dim3 grid(a.num_ctas, col_tiles);
-  if (a.warp_path && a.through_split) {
-    BwdThroughKernel<T, V, IdxT, WEIGHTED><<<grid, kBwdThreads, 0, stream>>>(a);
-    CountLaunch();
-  }
   if (a.warp_path && a.opt_kind == CUEMBED_OPT_SGD)
     BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_SGD>
         <<<grid, kBwdThreads, 0, stream>>>(a);
@@ -921,9 +916,6 @@ int LaunchBackwardImpl(const void* grad_y, int dtype, int embed_width,
   a.warp_path = warp_path ? 1 : 0;
   static const int own_env = EnvInt("CUEMBED_BWD_OWN", 1);
   a.own = own_env != 0 ? 1 : 0;
-  static const int through_env = EnvInt("CUEMBED_BWD_THROUGH", 1);
-  // the lean kernel assumes K is a multiple of 32 (it is: K = 32 * rounds)
-  a.through_split = (warp_path && through_env != 0 && nnz >= 64 * 1024) ? 1 : 0;
   a.opt_kind = opt.kind;
   a.opt_lr = opt.lr;
   a.opt_eps = opt.eps;

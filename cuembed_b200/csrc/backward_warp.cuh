@@ -117,13 +117,6 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
   int n = 0;
   if (c0 < a.nnz) n = static_cast<int>(min(static_cast<int64_t>(K), a.nnz - c0));
 
-  // Chunks that lie entirely inside one run that began earlier ("through"
-  // chunks: the interiors of hot rows, ~45 % of all chunks at the headline
-  // workload) are summed by BwdThroughKernel when a.through_split is set.
-  if (a.through_split && n == K && c0 > 0 &&
-      __ldg(keys + c0 - 1) == __ldg(keys + c0 + K - 1))
-    return;
-
   const int v = blockIdx.y * 32 + lane;
   const bool active = v < a.nvec;
   // base pointers that already hold this lane's column offset; opaque so that
@@ -373,83 +366,6 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
     a.meta_row[chunk * 2 + 1] = static_cast<long long>(tail_row);
     // work list of the fix-up (any order: every chain is summed on its own)
     if (has_tail) a.tail_list[1 + atomicAdd(a.tail_list, 1)] = chunk;
-  }
-}
-
-// A "through" chunk (all K nonzeros belong to one run that began in an earlier
-// chunk) is a plain sum of K grad_y rows into the chunk's fp32 head partial: no
-// run ends, no stores to the gradient, no inverse mapping.  Without that
-// bookkeeping the loop needs ~50 registers instead of 80, so 8 instead of 6
-// CTAs are resident per SM and the row gathers run close to the measured L2
-// gather ceiling; the general walker skips these chunks.  Same association
-// order as the walker (sequential inside the chunk), so results are identical.
-template <typename T, int V, typename IdxT, bool WEIGHTED>
-__global__ void __launch_bounds__(kBwdThreads, 8)
-    BwdThroughKernel(const BwdArgs a) {
-  using VecT = typename VecBits<V>::type;
-  constexpr int NW = V / 4;
-  constexpr int NE = NW * Elem<T>::kPerWord;
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int UNROLL = 8;
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
-  const IdxT* __restrict__ keys = static_cast<const IdxT*>(a.keys);
-  const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
-  const T* __restrict__ weights = static_cast<const T*>(a.weights);
-  const int K = a.chunk_nz;
-  const int64_t c0 = static_cast<int64_t>(chunk) * K;
-  if (c0 == 0 || c0 + K > a.nnz) return;
-  if (__ldg(keys + c0 - 1) != __ldg(keys + c0 + K - 1)) return;
-
-  uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
-  asm volatile("" : "+r"(row_bytes));
-  const int v = blockIdx.y * 32 + lane;
-  const bool active = v < a.nvec;
-  const char* gy = static_cast<const char*>(a.grad_y) +
-                   static_cast<int64_t>(active ? v : a.nvec - 1) * V;
-  asm volatile("" : "+l"(gy));
-
-  float acc[NE];
-#pragma unroll
-  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
-  IdxT sid_n = __ldg(sids + c0 + lane);
-  T w_n = T();
-  if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + lane);
-#pragma unroll 1
-  for (int r = 0; r * 32 < K; ++r) {
-    IdxT sid_r = sid_n;
-    T w_r = w_n;
-    if ((r + 1) * 32 < K) {
-      sid_n = __ldg(sids + c0 + (r + 1) * 32 + lane);
-      if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + (r + 1) * 32 + lane);
-    }
-    const int from = (lane + UNROLL) & 31;
-#pragma unroll 1
-    for (int jb = 0; jb < 32; jb += UNROLL) {
-      VecT vals[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-        vals[u] = LdgVec<V>(
-            RowAddr<IdxT>(gy, ShflIdx<IdxT>(sid_r, u, 32), row_bytes));
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if constexpr (WEIGHTED)
-          AccumulateVecWeighted<T, V>(vals[u], ShflWeight<T>(w_r, u), acc);
-        else
-          AccumulateVec<T, V>(vals[u], acc);
-      }
-      sid_r = ShflIdx<IdxT>(sid_r, from, 32);
-      if constexpr (WEIGHTED) w_r = ShflRaw<T>(w_r, from);
-    }
-  }
-  if (active)
-    StorePartial<NE>(
-        a.scratch + (static_cast<size_t>(chunk) * 2 + 0) * a.width + v * NE, acc);
-  if (lane == 0 && blockIdx.y == 0) {
-    a.meta[chunk * 2 + 0] = kHeadThrough;
-    a.meta[chunk * 2 + 1] = 0;
-    a.meta_row[chunk * 2 + 0] = 0;
-    a.meta_row[chunk * 2 + 1] = 0;
   }
 }
 
