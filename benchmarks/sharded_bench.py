@@ -175,7 +175,8 @@ def run_p2p(args, rank, local_rank, world):
     w, hot = cfg["embed_width"], cfg["hotness"]
     shard_rows = cfg["num_categories"]
     pdt = {"f32": torch.float32, "table": tdt}[getattr(args, "partial_dtype", "table")]
-    emb = PeerShardedEmbedding(table, rows, partial_dtype=pdt)
+    sf = {"auto": None, "on": True, "off": False}[getattr(args, "select_first", "auto")]
+    emb = PeerShardedEmbedding(table, rows, partial_dtype=pdt, select_first=sf)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
@@ -196,7 +197,8 @@ def run_p2p(args, rank, local_rank, world):
         dist.barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
-        out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum)
+        out, ctx = emb.forward(indices, None, None, batch, hot, ce.CombineMode.kSum,
+                               local_nnz=local_nnz if known_sizes else None)
         ev[1].record(stream)
         if known_sizes:
             pend = emb.backward_begin(grad_slice, ctx, True, local_nnz=local_nnz)
@@ -325,6 +327,7 @@ def run_p2p(args, rank, local_rank, world):
                                       f"slices pushed by copy engines during the local sort",
                        "transport": "p2p",
                        "l2": "flushed before every step (512 MB write)",
+                       "select_first": bool(emb.select_first),
                        "sizes": ("local nnz / num_unique known from an earlier identical step "
                                  "(--known-sizes): no host read-back" if known_sizes else
                                  "local nnz and num_unique read back by the host in every step "
@@ -334,7 +337,8 @@ def run_p2p(args, rank, local_rank, world):
                        "nvlink_bytes_out_per_rank": {"forward": nvlink_fwd, "backward": nvlink_bwd},
                        "peer_wait_status": status},
             "stages": {"forward": {"ms": round(fwd_ms, 4)},
-                       "select_sort_with_grad_push": {"ms": round(tr_ms, 4)},
+                       ("sort_with_grad_push" if emb.select_first else
+                        "select_sort_with_grad_push"): {"ms": round(tr_ms, 4)},
                        "backward": {"ms": round(bwd_ms, 4)}},
             "roofline": {"bound": "hbm", "kernel": "ShardPoolPushKernel + BwdSegReduceKernel (local)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

@@ -34,6 +34,7 @@
 // cannot get there before having seen that peer's next signal.
 // A wait that sees no signal for kWaitTimeoutNs gives up and raises the status
 // word instead of hanging the device.
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 

@@ -45,6 +45,7 @@ class PeerForwardContext:
     mode: CombineMode
     coo: Optional[tuple] = None
     local_nnz: int = -1
+    selected: Optional[tuple] = None   # (local_offsets, local_indices, sample_ids, local_weights)
 
 
 class PeerShardedEmbedding:
@@ -70,7 +71,8 @@ class PeerShardedEmbedding:
                  group: Optional[dist.ProcessGroup] = None,
                  partial_dtype: Optional[torch.dtype] = None,
                  rank: Optional[int] = None, world: Optional[int] = None,
-                 buffers: Optional[Callable] = None):
+                 buffers: Optional[Callable] = None,
+                 select_first: Optional[bool] = None):
         if not local_table.is_cuda:
             raise CuEmbedError("PeerShardedEmbedding needs CUDA tensors: there is no CPU path")
         self.group = group
@@ -85,6 +87,9 @@ class PeerShardedEmbedding:
         self.device = local_table.device
         self.partial_dtype = local_table.dtype if partial_dtype is None else partial_dtype
         self.ops = CudaLocalOps()
+        # from 4 ranks on, scanning the replicated index list once (selection)
+        # beats letting the pool-and-push kernel filter it (measured at N = 8)
+        self.select_first = (self.world >= 4) if select_first is None else bool(select_first)
         self._lib = _lib.load()
         self._buffers = buffers if buffers is not None else \
             (lambda kind, nbytes: peer.PeerBuffer(nbytes, group, self.device))
@@ -163,18 +168,28 @@ class PeerShardedEmbedding:
     # ------------------------------------------------------------- forward
     def forward(self, indices, offsets, weights, batch_size: int, num_hots: int,
                 mode: CombineMode = CombineMode.kSum,
-                out_dtype: Optional[torch.dtype] = None, stream=None):
+                out_dtype: Optional[torch.dtype] = None, stream=None,
+                local_nnz: Optional[int] = None):
         """Pooled lookup of the GLOBAL batch (replicated indices); returns this
         rank's slice [batch/world, width] (concat: [batch/world * hots, width])
         and the context for backward."""
         return self.forward_finish(self.forward_begin(
-            indices, offsets, weights, batch_size, num_hots, mode, out_dtype, stream))
+            indices, offsets, weights, batch_size, num_hots, mode, out_dtype, stream,
+            local_nnz=local_nnz))
 
     def forward_begin(self, indices, offsets, weights, batch_size: int, num_hots: int,
                       mode: CombineMode = CombineMode.kSum,
-                      out_dtype: Optional[torch.dtype] = None, stream=None):
+                      out_dtype: Optional[torch.dtype] = None, stream=None,
+                      local_nnz: Optional[int] = None):
         """Push phase (never waits for another rank).  Returns a pending handle
-        for forward_finish."""
+        for forward_finish.
+
+        With `select_first` (default from 4 ranks on) the rank first selects its
+        own lookups from the replicated index list (one pass, also what the
+        backward needs) and the pool-and-push kernel then walks only those; with
+        fewer ranks the push kernel filters the replicated list itself.
+        `local_nnz`: the number of lookups this rank owns, if the caller knows
+        it (saves the host read that sizes the selection)."""
         if batch_size % self.world != 0:
             raise ValueError("batch_size must be divisible by the number of ranks")
         if weights is not None and weights.dtype != self.table.dtype:
@@ -195,16 +210,31 @@ class PeerShardedEmbedding:
         base = (epoch & 1) * one
         slot_ptrs = peer.ptr_array(buf.ptrs, base + self.rank * per * width * psize)
         counts = torch.empty(batch_size, dtype=torch.int32, device=self.device)
+        push_idx, push_off, push_w, push_hots = indices, offsets, weights, num_hots
+        lo, hi = self.lo, self.hi
+        selected = None
+        if self.select_first:
+            # The push kernel at N ranks would scan N x its share of indices; the
+            # selection scans them once for forward AND backward.
+            concat_w = weights
+            selected = self.ops.shard_select_coo(indices, offsets, concat_w, batch_size,
+                                                 num_hots, self.lo, self.hi, counts=None,
+                                                 nnz_cap=local_nnz)
+            push_off, push_idx, _, push_w = selected
+            push_hots, lo, hi = 0, 0, self.hi - self.lo
         _check(lib.cuembed_shard_pool_push(
             _dev(self.table, "table"), _dt(self.table), width,
-            _dev(indices, "indices"), _it(indices), _dev(offsets, "offsets"),
-            _it(offsets) if offsets is not None else 0, _dev(weights, "weights"),
-            batch_size, num_hots, self.lo, self.hi, slot_ptrs, self.world, self.rank,
+            _dev(push_idx, "indices"), _it(push_idx), _dev(push_off, "offsets"),
+            _it(push_off) if push_off is not None else 0, _dev(push_w, "weights"),
+            batch_size, push_hots, lo, hi, slot_ptrs, self.world, self.rank,
             _dt(torch.empty(0, dtype=self.partial_dtype)), _dev(counts, "counts"),
             _stream(stream)))
         self._signal(CH_FORWARD, epoch, stream)
         ctx = PeerForwardContext(indices, offsets, weights, counts, batch_size,
                                  num_hots, mode)
+        ctx.selected = selected
+        if selected is not None and local_nnz is not None:
+            ctx.local_nnz = int(local_nnz)
         return ("pool", ctx, buf, base, epoch, out_dtype, stream)
 
     def forward_finish(self, pending):
@@ -283,10 +313,16 @@ class PeerShardedEmbedding:
                 raise CuEmbedError("sharded concat backward needs nnz < 2^31")
             weights = torch.arange(ctx.indices.numel(), dtype=torch.int32,
                                    device=self.device).view(torch.float32)
-        l_off, l_idx, l_sid, l_w = self.ops.shard_select_coo(
-            ctx.indices, ctx.offsets, weights, ctx.batch, ctx.num_hots, self.lo, self.hi,
-            counts=ctx.counts, nnz_cap=local_nnz)
-        ctx.local_nnz = int(l_off[-1].item()) if local_nnz is None else int(local_nnz)
+        if ctx.selected is not None and not concat:
+            l_off, l_idx, l_sid, l_w = ctx.selected   # selected before the forward
+        else:
+            l_off, l_idx, l_sid, l_w = self.ops.shard_select_coo(
+                ctx.indices, ctx.offsets, weights, ctx.batch, ctx.num_hots, self.lo,
+                self.hi, counts=ctx.counts, nnz_cap=local_nnz)
+        if local_nnz is not None:
+            ctx.local_nnz = int(local_nnz)
+        elif ctx.local_nnz < 0:
+            ctx.local_nnz = int(l_off[-1].item())
         if ctx.local_nnz == 0:
             ctx.coo = ()
             return

@@ -325,6 +325,7 @@ int cuembed_shard_wait(const void* flags, int world, int channel,
                        cuembed_stream_t stream);
 int cuembed_shard_set_timeout_ms(long long timeout_ms);
 
+
 /*
  * Forward, step 2 (on the bag owner): wait for all ranks, then
  * out[s, :] = cast(scale * (slot 0 + slot 1 + ... in rank order)) for the
