@@ -896,7 +896,7 @@ def main():
                     help="N > 1: write a CUPTI per-kernel time table of 5 extra steps here")
     ap.add_argument("--select-first", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: select the rank's own lookups before the forward "
-                         "(auto: from 4 ranks on)")
+                         "(auto = off: measured slower on the weak-scaled C2 shards)")
     ap.add_argument("--known-sizes", action="store_true",
                     help="N > 1: reuse local nnz / num_unique of an earlier identical step "
                          "instead of reading them back every step")

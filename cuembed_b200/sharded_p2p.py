@@ -87,9 +87,12 @@ class PeerShardedEmbedding:
         self.device = local_table.device
         self.partial_dtype = local_table.dtype if partial_dtype is None else partial_dtype
         self.ops = CudaLocalOps()
-        # from 4 ranks on, scanning the replicated index list once (selection)
-        # beats letting the pool-and-push kernel filter it (measured at N = 8)
-        self.select_first = (self.world >= 4) if select_first is None else bool(select_first)
+        # opt-in: select the rank's own lookups BEFORE the forward (one scan of
+        # the replicated index list for forward and backward).  Measured at
+        # N = 8: 5 % faster on C5 (width 128, one global table), 10 % slower on
+        # the weak-scaled C2 shards -- so the default lets the pool-and-push
+        # kernel filter the list itself.
+        self.select_first = bool(select_first) if select_first is not None else False
         self._lib = _lib.load()
         self._buffers = buffers if buffers is not None else \
             (lambda kind, nbytes: peer.PeerBuffer(nbytes, group, self.device))
@@ -184,7 +187,7 @@ class PeerShardedEmbedding:
         """Push phase (never waits for another rank).  Returns a pending handle
         for forward_finish.
 
-        With `select_first` (default from 4 ranks on) the rank first selects its
+        With `select_first` (constructor option, off by default) the rank first selects its
         own lookups from the replicated index list (one pass, also what the
         backward needs) and the pool-and-push kernel then walks only those; with
         fewer ranks the push kernel filters the replicated list itself.

@@ -86,7 +86,8 @@ def expected_forward(p, world, oracle, out_np_dtype=None):
     return total
 
 
-def run_virtual(p, world, oracle, partial_dtype=torch.float32, steps=1, compressed=True):
+def run_virtual(p, world, oracle, partial_dtype=torch.float32, steps=1, compressed=True,
+                select_first=None):
     """`steps` forward + backward rounds on `world` virtual ranks of cuda:0.
     Returns per-step lists of (outs, grads, rows)."""
     import gpu_helpers as gh
@@ -110,7 +111,7 @@ def run_virtual(p, world, oracle, partial_dtype=torch.float32, steps=1, compress
         lo, hi = row_range(p.num_categories, world, r)
         embs.append(PeerShardedEmbedding(table[lo:hi].contiguous(), p.num_categories,
                                          partial_dtype=partial_dtype, rank=r, world=world,
-                                         buffers=factory(r)))
+                                         buffers=factory(r), select_first=select_first))
     idx, off, w = gh.to_dev(p.indices), gh.to_dev(p.offsets), gh.to_dev(p.weights)
     gy = gh.to_dev(p.grad_y)
     mode = CombineMode(p.mode)
@@ -211,6 +212,24 @@ def test_virtual_ranks_16bit_partials(cuda_lib, oracle):
     ref = to_f32(p.cpu_forward(oracle, out_dt=F32))
     # every partial is rounded to fp16 once more: <= world/2 + 1/2 ulp of the terms
     assert np.all(np.abs(got - ref) <= 2 ** -10 * 4 * np.maximum(1.0, np.abs(ref)))
+
+
+@pytest.mark.gpu
+def test_virtual_ranks_select_first(cuda_lib, oracle):
+    """select_first: the rank selects its own lookups before the forward and the
+    pool-and-push kernel walks the selection (CSR bags of owned, rebased
+    indices); identical results, forward and backward."""
+    p = Problem(96, 64, 20, "mean", csr=True, weighted=True, compressed=True,
+                num_categories=700, dt=F32, seed=69, integer_table=True)
+    base = run_virtual(p, 4, oracle, select_first=False)[0]
+    sel = run_virtual(p, 4, oracle, select_first=True, steps=2)
+    for outs, grads, rows, _ in sel:
+        for a, b in zip(outs, base[0]):
+            assert helpers.bits_equal(a, b)
+        for a, b in zip(grads, base[1]):
+            assert helpers.bits_equal(a, b)
+        for a, b in zip(rows, base[2]):
+            assert np.array_equal(a, b)
 
 
 @pytest.mark.gpu
