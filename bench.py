@@ -682,6 +682,47 @@ def run_gpu(args):
         extras["reference_gpu_same_box"] = rg
         ceilings = measure_gather_ceilings(torch, dev, table, grad_y, indices, t_sid, flush)
         extras["gather_ceilings"] = ceilings
+        # ---- the hot-row policy of north_star, measured: forward with a
+        # shared-memory cache of the rows hit >= nnz / 4096 times in this batch
+        # (list built on the device from the transposed indices)
+        cap = ce.forward_hot_capacity(tdt, w)
+        if cap > 0 and idt == torch.int32:
+            hot_rows, hot_count = ce.HotRowsFromSorted(t_idx, nnz, max(2, nnz // 4096), cap)
+            out_hot = torch.empty_like(out)
+
+            def forward_hot():
+                ce.EmbeddingForwardHot(table, w, indices, None, None, batch, hot,
+                                       ce.CombineMode.kSum, out_hot, hot_rows, hot_count)
+
+            def hot_list():
+                ce.HotRowsFromSorted(t_idx, nnz, max(2, nnz // 4096), cap)
+
+            tms = {}
+            for name, fn in (("forward_hot", forward_hot), ("hot_list", hot_list)):
+                for _ in range(3):
+                    fn()
+                tot = 0.0
+                for _ in range(args.steps):
+                    flush.fill_(1)
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    fn()
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    tot += e0.elapsed_time(e1)
+                tms[name] = tot / args.steps
+            forward()
+            torch.cuda.synchronize()
+            extras["forward_hot_row_cache"] = {
+                "ms": round(tms["forward_hot"], 4), "plain_forward_ms": round(per_stage["forward"], 4),
+                "hot_list_ms": round(tms["hot_list"], 4),
+                "rows_cached": int(min(int(hot_count.item()), cap)), "capacity": cap,
+                "min_count": max(2, nnz // 4096),
+                "bit_identical_to_plain_forward": bool(torch.equal(out_hot, out)),
+                "note": "cuembed_forward_hot: rows hit >= min_count times kept in shared memory "
+                        "(one 1024-thread CTA per SM, hash probe per index); list from the "
+                        "transposed indices of the same batch"}
 
     e2e_ms, h2d, d2h = float("nan"), 0, 0
     if not args.no_e2e:

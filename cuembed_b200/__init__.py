@@ -11,11 +11,13 @@ from .api import (OPT_ADAGRAD, OPT_SGD, CombineMode, ComputeCompressedGradIndice
                   EmbeddingBackward, EmbeddingBackwardUpdate, EmbeddingForward,
                   EmbeddingForwardMulti, ExtractRowIdsForConcat,
                   ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, ShardFinalize,
-                  ShardSelect, Transpose, backward_workspace_bytes, launch_count)
+                  ShardSelect, Transpose, backward_workspace_bytes, launch_count,
+                  EmbeddingForwardHot, HotRowsFromSorted, forward_hot_capacity)
 
 __all__ = [
     "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward", "EmbeddingBackwardUpdate", "EmbeddingForwardMulti", "OPT_SGD", "OPT_ADAGRAD",
     "ExtractRowIdsFromFixed", "ExtractRowIdsFromCSR", "ExtractRowIdsForConcat",
     "Transpose", "ComputeCompressedGradIndices", "backward_workspace_bytes",
-    "launch_count", "ShardSelect", "ShardFinalize",
+    "launch_count", "ShardSelect", "ShardFinalize", "EmbeddingForwardHot", "HotRowsFromSorted",
+    "forward_hot_capacity",
 ]

@@ -26,6 +26,10 @@ SIGNATURES = {
                                     ctypes.POINTER(_vp), ctypes.POINTER(_ci),
                                     ctypes.POINTER(_ci), ctypes.POINTER(_ci),
                                     ctypes.POINTER(_vp), _ci, ctypes.c_longlong, _vp]),
+    "cuembed_forward_hot_capacity": (_ci, [_ci, _ci]),
+    "cuembed_forward_hot": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci, _ci,
+                                  _vp, _ci, _vp, _vp, _ci, _vp]),
+    "cuembed_hot_rows_from_sorted": (_ci, [_vp, _ci, _ci, _ci, _vp, _ci, _vp, _vp]),
     "cuembed_extract_row_ids_fixed": (_ci, [_ci, _ci, _vp, _ci, _vp]),
     "cuembed_extract_row_ids_csr": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp]),
     "cuembed_extract_row_ids_concat": (_ci, [_ci, _vp, _ci, _vp]),

@@ -98,6 +98,47 @@ def EmbeddingForward(params: torch.Tensor, embed_width: int,
         int(bool(fp16_math)), _dev(ret, "ret"), _dt(ret), _stream(stream)))
 
 
+def forward_hot_capacity(dtype: torch.dtype, embed_width: int) -> int:
+    """Rows the shared-memory hot-row cache of EmbeddingForwardHot holds for this
+    row shape (0: shape not supported)."""
+    return int(_lib.load().cuembed_forward_hot_capacity(_DT[dtype], int(embed_width)))
+
+
+def HotRowsFromSorted(sorted_keys: torch.Tensor, nnz: int, min_count: int,
+                      capacity: int, stream=None):
+    """Rows hit at least `min_count` times in a sorted (transposed) index array:
+    returns (hot_rows int32 [capacity], hot_count int32 [1]) on the device."""
+    lib = _lib.load()
+    hot_rows = torch.full((max(capacity, 1),), -1, dtype=torch.int32, device=sorted_keys.device)
+    hot_count = torch.zeros(1, dtype=torch.int32, device=sorted_keys.device)
+    _check(lib.cuembed_hot_rows_from_sorted(
+        _dev(sorted_keys, "sorted_keys"), _it(sorted_keys), int(nnz), int(min_count),
+        _dev(hot_rows, "hot_rows"), int(capacity), _dev(hot_count, "hot_count"),
+        _stream(stream)))
+    return hot_rows, hot_count
+
+
+def EmbeddingForwardHot(params: torch.Tensor, embed_width: int, indices: torch.Tensor,
+                        offsets: Optional[torch.Tensor], weights: Optional[torch.Tensor],
+                        batch_size: int, num_hots: int, mode: CombineMode,
+                        ret: torch.Tensor, hot_rows: torch.Tensor, hot_count: torch.Tensor,
+                        stream=None) -> None:
+    """cuembed_forward_hot: EmbeddingForward with a shared-memory cache of the
+    rows listed in `hot_rows[:hot_count]` (int32, device).  Bit-identical to
+    EmbeddingForward for any list; int32 indices, rows of 128 / 256 / 512 bytes."""
+    lib = _lib.load()
+    if weights is not None and weights.dtype != params.dtype:
+        raise CuEmbedError("weights must have the element type of the table")
+    if hot_rows.dtype != torch.int32 or hot_count.dtype != torch.int32:
+        raise CuEmbedError("hot_rows / hot_count must be int32")
+    _check(lib.cuembed_forward_hot(
+        _dev(params, "params"), _dt(params), int(embed_width), _dev(indices, "indices"),
+        _it(indices), _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+        _dev(weights, "weights"), int(batch_size), int(num_hots), int(mode),
+        _dev(ret, "ret"), _dt(ret), _dev(hot_rows, "hot_rows"), _dev(hot_count, "hot_count"),
+        int(hot_rows.numel()), _stream(stream)))
+
+
 def ExtractRowIdsFromFixed(batch_size: int, num_hots: int,
                            row_ids: torch.Tensor, stream=None) -> None:
     """cuembed/include/index_transforms.cuh:45-55."""

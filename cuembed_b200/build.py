@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcuembed_b200.so")
 SOURCES = ["c_api.cu", "forward.cu", "transforms.cu", "backward.cu", "sharded.cu",
-           "sharded_p2p.cu", "microbench.cu"]
+           "sharded_p2p.cu", "microbench.cu", "forward_hot.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,12 +18,21 @@
 
 namespace cuembed_b200 {
 
-template <int G, bool NO_L1, int UNROLL = 8>
+// POLICY: rows are loaded with an L2 evict_last cache hint and the index list
+// with evict_first (createpolicy + ld.global.nc.L2::cache_hint) -- the per-load
+// form of an L2 access-policy window, which cannot be an address window here
+// because hot rows are scattered over the table.
+template <int G, bool NO_L1, int UNROLL = 8, bool POLICY = false>
 __global__ void __launch_bounds__(kCtaThreads, (UNROLL <= 8 ? 4 : 2))
     GatherRowsKernel(const char* __restrict__ buf, uint32_t row_bytes,
                      const int* __restrict__ rows, long long n,
                      unsigned* __restrict__ sink) {
   constexpr unsigned kFull = 0xffffffffu;
+  uint64_t pol_last = 0, pol_first = 0;
+  if constexpr (POLICY) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  }
   const int lane = threadIdx.x & 31;
   const int lane_g = lane & (G - 1);
   const int gw = lane / G;                     // lane group within the warp
@@ -35,7 +44,15 @@ __global__ void __launch_bounds__(kCtaThreads, (UNROLL <= 8 ? 4 : 2))
   uint32_t acc = 0;
   // a warp takes 32 consecutive index entries per round
   for (long long i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
-    const int my = (i0 + lane < n) ? __ldg(rows + i0 + lane) : 0;
+    int my = 0;
+    if (i0 + lane < n) {
+      if constexpr (POLICY)
+        asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;"
+                     : "=r"(my)
+                     : "l"(rows + i0 + lane), "l"(pol_first));
+      else
+        my = __ldg(rows + i0 + lane);
+    }
 #pragma unroll 1
     for (int jb = 0; jb < 32; jb += UNROLL * GPW) {
       uint4 v[UNROLL];
@@ -43,7 +60,12 @@ __global__ void __launch_bounds__(kCtaThreads, (UNROLL <= 8 ? 4 : 2))
       for (int u = 0; u < UNROLL; ++u) {
         const int r = __shfl_sync(kFull, my, jb + u * GPW + gw);
         const char* p = base + static_cast<uint64_t>(static_cast<uint32_t>(r)) * row_bytes;
-        if constexpr (NO_L1) {
+        if constexpr (POLICY) {
+          asm volatile(
+              "ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+              : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+              : "l"(p), "l"(pol_last));
+        } else if constexpr (NO_L1) {
           asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                        : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
                        : "l"(p));
@@ -212,7 +234,11 @@ extern "C" int cuembed_microbench_gather(const void* buf, int row_bytes,
       GatherRowsKernel<GG, false><<<grid, kCtaThreads, 0, stream>>>(            \
           b, static_cast<uint32_t>(row_bytes), rows, n, sink);                  \
   } while (0)
-  if (row_bytes == 512 && no_l1_allocate == 2) {
+  if (row_bytes == 512 && no_l1_allocate == 3) {
+    // L2 evict_last on the rows, evict_first on the index list
+    GatherRowsKernel<32, false, 8, true><<<grid, kCtaThreads, 0, stream>>>(
+        b, static_cast<uint32_t>(row_bytes), rows, n, sink);
+  } else if (row_bytes == 512 && no_l1_allocate == 2) {
     // deeper pipeline: 16 rows in flight per warp, 2 CTAs per SM
     GatherRowsKernel<32, false, 16><<<GetDeviceInfo().sm_count * 2, kCtaThreads, 0, stream>>>(
         b, static_cast<uint32_t>(row_bytes), rows, n, sink);

@@ -113,6 +113,30 @@ int cuembed_forward_multi(int num_tables, const void* const* params,
                           void* const* rets, int out_dtype,
                           long long out_row_stride, cuembed_stream_t stream);
 
+/*
+ * Pooled lookup with a shared-memory cache of hot table rows (new; the
+ * power-law policy of BASELINE.json's north_star, measured in
+ * profiles/r02_notes.md).  hot_rows [capacity] int32 row ids and *hot_count
+ * (device int32, clamped to capacity) name the rows to keep in shared memory;
+ * any list is correct (rows not in the batch, duplicates, negative entries are
+ * ignored), a good one holds the most frequent rows of the batch --
+ * cuembed_hot_rows_from_sorted derives it from the sorted indices of a
+ * transposed batch (rows hit >= min_count times).  Results are bit-identical
+ * to cuembed_forward.  Scope: row bytes 128 / 256 / 512, int32 indices, sum or
+ * mean; cuembed_forward_hot_capacity returns the number of rows that fit (0:
+ * shape not supported, use cuembed_forward).
+ */
+int cuembed_forward_hot_capacity(int in_dtype, int embed_width);
+int cuembed_forward_hot(const void* params, int in_dtype, int embed_width,
+                        const void* indices, int idx_type, const void* offsets,
+                        int off_type, const void* weights, int batch_size,
+                        int num_hots, int mode, void* ret, int out_dtype,
+                        const int* hot_rows, const int* hot_count, int capacity,
+                        cuembed_stream_t stream);
+int cuembed_hot_rows_from_sorted(const void* sorted_keys, int idx_type, int nnz,
+                                 int min_count, int* hot_rows, int capacity,
+                                 int* hot_count, cuembed_stream_t stream);
+
 /* row_ids[i] = i / num_hots, nnz = batch_size * num_hots. */
 int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
                                   int idx_type, cuembed_stream_t stream);
@@ -357,7 +381,8 @@ int cuembed_shard_allgather_push(const void* src, size_t bytes,
  * beyond one XOR per word.  On an L2-resident buffer this is the L2 -> SM
  * gather ceiling, on a multi-GB buffer the DRAM gather ceiling.
  * no_l1_allocate: 1 = ld.global.nc.L1::no_allocate, 2 = 16 rows in flight per
- * warp (512-byte rows only).  sink: 4 bytes.
+ * warp, 3 = L2 cache hints (evict_last on rows, evict_first on the index list);
+ * 2 and 3 for 512-byte rows only.  sink: 4 bytes.
  */
 int cuembed_microbench_gather(const void* buf, int row_bytes, const int* rows,
                               long long n, int no_l1_allocate, unsigned* sink,

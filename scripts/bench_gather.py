@@ -51,7 +51,8 @@ streams = {"l2_random": (grad_y, rnd, False), "bwd_stream": (grad_y, t_sid, True
 out = {}
 for name, (buf, idx, fl) in streams.items():
     res = {}
-    for mode, label in ((0, "ldg_8x32warps"), (2, "ldg_16x16warps")):
+    for mode, label in ((0, "ldg_8x32warps"), (2, "ldg_16x16warps"), (1, "ldg_L1_no_allocate"),
+                        (3, "ldg_L2_evict_last_rows_evict_first_indices")):
         res[label] = run(lambda: lib.cuembed_microbench_gather(
             buf.data_ptr(), 512, idx.data_ptr(), nnz, mode, sink.data_ptr(), stream.cuda_stream), fl)
     for v, label in ((0, "bulk_32x2x6"), (1, "bulk_16x3x8"), (2, "bulk_32x1x12"),

@@ -448,6 +448,49 @@ def test_backward_hot_rows_real_valued_and_deterministic(cuda_lib, oracle):
         assert bits_equal(g2, g_grad)
 
 
+@pytest.mark.parametrize("width,dt,csr,weighted,mode", [
+    (256, F16, False, False, "sum"),    # the headline row shape: 512-byte rows
+    (64, F32, True, True, "mean"),      # 256-byte fp32 rows, CSR, weighted mean
+    (128, BF16, False, True, "sum"),    # 256-byte bf16 rows, weighted
+    (64, F16, True, False, "mean"),     # 128-byte rows (4-byte vectors), CSR mean
+])
+def test_forward_hot_row_cache_is_bit_identical(cuda_lib, oracle, width, dt, csr, weighted, mode):
+    """cuembed_forward_hot keeps the listed rows in shared memory; accumulation
+    order and arithmetic are those of cuembed_forward, so the output must be
+    bit-identical to the oracle for ANY list: the real hot rows of the batch
+    (from the transposed indices), an empty list, and a list of unrelated rows
+    with duplicates and negative entries."""
+    p = Problem(3000, width, 24, mode, csr=csr, weighted=weighted, dt=dt,
+                num_categories=6000, alpha=1.15, seed=83)
+    want = p.cpu_forward(oracle)
+    tdt = gh.TORCH_DT[dt]
+    cap = ce.forward_hot_capacity(tdt, width)
+    assert cap > 0
+    _, t_idx, _, _, _ = gh.gpu_transpose(p)
+    hot_rows, hot_count = ce.HotRowsFromSorted(t_idx, p.nnz, 8, cap)
+    torch.cuda.synchronize()
+    n_hot = int(hot_count.item())
+    assert n_hot > 10, "the power-law batch has rows with >= 8 hits"
+    # every listed row really has >= 8 hits
+    counts = np.bincount(p.indices, minlength=p.num_categories)
+    listed = hot_rows[:min(n_hot, cap)].cpu().numpy()
+    assert (counts[listed] >= 8).all() and len(set(listed.tolist())) == len(listed)
+    rng = np.random.default_rng(5)
+    junk = torch.from_numpy(np.r_[rng.integers(0, p.num_categories, 40), [-1, -5],
+                                  rng.integers(0, 50, 30)].astype(np.int32)).to(gh.DEV)
+    lists = [(hot_rows, hot_count),
+             (hot_rows, torch.zeros(1, dtype=torch.int32, device=gh.DEV)),
+             (junk, torch.tensor([junk.numel()], dtype=torch.int32, device=gh.DEV))]
+    for rows_t, count_t in lists:
+        ret = torch.full((p.batch, width), float("nan"), dtype=tdt, device=gh.DEV)
+        ce.EmbeddingForwardHot(gh.to_dev(p.table), width, gh.to_dev(p.indices),
+                               gh.to_dev(p.offsets), gh.to_dev(p.weights), p.batch,
+                               p.num_hots, ce.CombineMode(p.mode), ret, rows_t, count_t)
+        torch.cuda.synchronize()
+        got = gh.to_host(ret)
+        assert bits_equal(got, want), _diff(got, want, f"hot cache, list of {int(count_t.item())}")
+
+
 @pytest.mark.parametrize("dt", DTS)
 def test_forward_multi_table(cuda_lib, oracle, dt):
     """cuembed_forward_multi: 35 tables (two launches of
