@@ -427,8 +427,7 @@ def run_e2e(args, ce, torch, dev, tdt, idt, cfg, idx_host, table, num_unique, wo
             s_k.wait_event(s.out_done)     # step i-2's results have left the device
             ce.EmbeddingForward(table, w, s.indices, None, None, batch, hot,
                                 ce.CombineMode.kSum, s.out)
-            ce.ExtractRowIdsFromFixed(batch, hot, s.row_ids)
-            ce.Transpose(s.row_ids, s.indices, None, nnz, s.t_idx, s.t_sid, None, work)
+            ce.TransposeFixed(s.indices, None, batch, hot, s.t_idx, s.t_sid, None, work)
             nu = 0
             if fused_sgd:
                 # the gradient is consumed on the device: SGD step on the table
@@ -530,8 +529,15 @@ def run_gpu(args):
                             ce.CombineMode.kSum, out)
 
     def transpose():
-        ce.ExtractRowIdsFromFixed(batch, hot, row_ids)
-        ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+        # fixed-hotness COO: the sample ids (position / hotness) are synthesised in
+        # the first sort pass (cuembed_transpose_fixed) instead of being written
+        # by ExtractRowIdsFromFixed and read back; --separate-row-ids times the
+        # reference's three-call sequence
+        if args.separate_row_ids:
+            ce.ExtractRowIdsFromFixed(batch, hot, row_ids)
+            ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+        else:
+            ce.TransposeFixed(indices, None, batch, hot, t_idx, t_sid, None, work)
         ce.ComputeCompressedGradIndices(t_idx, nnz, remapped, work)
 
     # first pass to learn num_unique (the caller reads remapped.back()+1 on the
@@ -624,8 +630,7 @@ def run_gpu(args):
     extras = {}
     if not args.no_extras:
         def transpose_nc():
-            ce.ExtractRowIdsFromFixed(batch, hot, row_ids)
-            ce.Transpose(row_ids, indices, None, nnz, t_idx, t_sid, None, work)
+            ce.TransposeFixed(indices, None, batch, hot, t_idx, t_sid, None, work)
 
         def update():
             ce.EmbeddingBackwardUpdate(grad_y, w, nnz, t_idx, t_sid, None, ce.OPT_SGD,
@@ -750,7 +755,7 @@ def run_gpu(args):
     hbm_peak, hbm_src = measured_peaks()
     by = stage_bytes(cfg, nnz, num_unique)
     dominant = max(("forward", "backward"), key=lambda k: per_stage[k])
-    kernel_name = {"forward": "FwdPoolKernel", "backward": "BwdSegReduceKernel"}[dominant]
+    kernel_name = {"forward": "FwdPoolKernel", "backward": "BwdWarpKernel"}[dominant]
     achieved = by[dominant] / (per_stage[dominant] * 1e-3) / 1e9
     es_ = 2 if cfg["dtype"] in ("f16", "bf16") else 4
     isz_ = 4 if cfg["index"] == "int32" else 8
@@ -839,6 +844,10 @@ def run_gpu(args):
                                f"alpha {cfg['alpha']}, {cfg['index']} indices, sum, compressed grad",
                    "l2": "flushed before every stage (512 MB write)",
                    "launch": launch_mode,
+                   "transpose": ("ExtractRowIdsFromFixed + Transpose + ComputeCompressedGradIndices"
+                                 if args.separate_row_ids else
+                                 "cuembed_transpose_fixed (row ids synthesised in the first sort "
+                                 "pass) + ComputeCompressedGradIndices"),
                    "frac_of_hbm_peak": "SURVEY 8(d) accounting (the reference's algorithmic bytes / "
                                        "stage time / measured HBM copy bandwidth): counts every "
                                        "gathered row, most of which are L2 hits, so it can exceed "
@@ -929,6 +938,9 @@ def main():
     ap.add_argument("--cpu-sample-bags", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--separate-row-ids", action="store_true",
+                    help="transpose stage as ExtractRowIdsFromFixed + Transpose (the "
+                         "reference's call sequence) instead of cuembed_transpose_fixed")
     ap.add_argument("--no-graphs", action="store_true",
                     help="launch the stages directly instead of replaying CUDA graphs")
     ap.add_argument("--no-extras", action="store_true",

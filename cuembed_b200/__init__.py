@@ -12,12 +12,13 @@ from .api import (OPT_ADAGRAD, OPT_SGD, CombineMode, ComputeCompressedGradIndice
                   EmbeddingForwardMulti, ExtractRowIdsForConcat,
                   ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, ShardFinalize,
                   ShardSelect, Transpose, backward_workspace_bytes, launch_count,
-                  EmbeddingForwardHot, HotRowsFromSorted, forward_hot_capacity)
+                  EmbeddingForwardHot, HotRowsFromSorted, forward_hot_capacity,
+                  TransposeFixed)
 
 __all__ = [
     "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward", "EmbeddingBackwardUpdate", "EmbeddingForwardMulti", "OPT_SGD", "OPT_ADAGRAD",
     "ExtractRowIdsFromFixed", "ExtractRowIdsFromCSR", "ExtractRowIdsForConcat",
     "Transpose", "ComputeCompressedGradIndices", "backward_workspace_bytes",
     "launch_count", "ShardSelect", "ShardFinalize", "EmbeddingForwardHot", "HotRowsFromSorted",
-    "forward_hot_capacity",
+    "forward_hot_capacity", "TransposeFixed",
 ]

@@ -35,6 +35,7 @@ SIGNATURES = {
     "cuembed_extract_row_ids_concat": (_ci, [_ci, _vp, _ci, _vp]),
     "cuembed_transpose": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp,
                                 _vp, _szp, _vp]),
+    "cuembed_transpose_fixed": (_ci, [_vp, _ci, _ci, _vp, _ci, _ci, _vp, _vp, _vp, _vp, _szp, _vp]),
     "cuembed_compressed_grad_indices": (_ci, [_vp, _ci, _ci, _vp, _vp, _szp, _vp]),
     "cuembed_backward": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp,
                                _ci, _vp, _vp, _vp]),

@@ -190,6 +190,26 @@ def Transpose(rows: torch.Tensor, cols: torch.Tensor,
     return int(lwork.value)
 
 
+def TransposeFixed(cols: torch.Tensor, weights: Optional[torch.Tensor],
+                   batch_size: int, num_hots: int,
+                   transpose_rows: torch.Tensor, transpose_cols: torch.Tensor,
+                   transpose_weights: Optional[torch.Tensor],
+                   work: torch.Tensor, stream=None) -> None:
+    """cuembed_transpose_fixed: ExtractRowIdsFromFixed + Transpose in one call
+    (the sample ids position / num_hots are synthesised in the first sort pass;
+    no row-id array).  `work` sized by Transpose(..., work=None) for
+    nnz = batch_size * num_hots."""
+    lib = _lib.load()
+    lwork = ctypes.c_size_t(work.numel())
+    wdt = _dt(weights) if weights is not None else 0
+    _check(lib.cuembed_transpose_fixed(
+        _dev(cols, "cols"), int(batch_size), int(num_hots), _dev(weights, "weights"), wdt,
+        _it(cols), _dev(transpose_rows, "transpose_rows"),
+        _dev(transpose_cols, "transpose_cols"),
+        _dev(transpose_weights, "transpose_weights"), _dev(work, "work"),
+        ctypes.byref(lwork), _stream(stream)))
+
+
 def ComputeCompressedGradIndices(indices: torch.Tensor, nnz: int,
                                  remapped_indices: Optional[torch.Tensor],
                                  work: Optional[torch.Tensor], stream=None) -> int:

@@ -111,6 +111,17 @@ int cuembed_transpose(const void* rows, const void* cols, const void* weights,
                          work, lwork, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int cuembed_transpose_fixed(const void* cols, int batch_size, int num_hots,
+                            const void* weights, int weight_dtype, int idx_type,
+                            void* transpose_rows, void* transpose_cols,
+                            void* transpose_weights, char* work, size_t* lwork,
+                            cuembed_stream_t stream) {
+  return LaunchTransposeFixed(cols, batch_size, num_hots, weights, weight_dtype,
+                              idx_type, transpose_rows, transpose_cols,
+                              transpose_weights, work, lwork,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
 int cuembed_compressed_grad_indices(const void* indices, int idx_type, int nnz,
                                     void* remapped_indices, char* work,
                                     size_t* lwork, cuembed_stream_t stream) {

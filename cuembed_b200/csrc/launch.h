@@ -40,6 +40,12 @@ int LaunchTranspose(const void* rows, const void* cols, const void* weights,
                     void* transpose_weights, char* work, size_t* lwork,
                     cudaStream_t stream);
 
+int LaunchTransposeFixed(const void* cols, int batch_size, int num_hots,
+                         const void* weights, int weight_dtype, int idx_type,
+                         void* transpose_rows, void* transpose_cols,
+                         void* transpose_weights, char* work, size_t* lwork,
+                         cudaStream_t stream);
+
 int LaunchCompressedGradIndices(const void* indices, int idx_type, int nnz,
                                 void* remapped, char* work, size_t* lwork,
                                 cudaStream_t stream);

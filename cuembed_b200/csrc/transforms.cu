@@ -312,6 +312,10 @@ struct SortArgs {
   int nnz;
   int num_tiles;
   int pass;  // byte position handled by this launch
+  // > 0: the payload of the input is not read but synthesised in the first live
+  // pass as position / synth_hots (fixed-hotness sample ids: the fused
+  // transpose entry point, no row-id array)
+  int synth_hots;
 };
 
 __device__ __forceinline__ uint32_t LdVolatile(const uint32_t* p) {
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * kCtaThreads + tid;
          i < a.nnz; i += static_cast<int64_t>(gridDim.x) * kCtaThreads) {
       kout[i] = kin[i];
-      vout[i] = vin[i];
+      vout[i] = a.synth_hots > 0 ? static_cast<KeyT>(i / a.synth_hots) : vin[i];
       if constexpr (WBYTES != 0)
         static_cast<WT*>(a.w_out)[i] = static_cast<const WT*>(a.w_in)[i];
     }
@@ -440,10 +444,31 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
       const int local = warp_base + i * 32 + lane;
       key[i] = local < tile_n ? kin[tile_base + local] : KeyT(0);
     }
+    if (ordinal == 0 && a.synth_hots > 0) {
+      // sample id = position / hotness: one division per tile and thread, then
+      // 32 positions further per item
+      const uint32_t hots = static_cast<uint32_t>(a.synth_hots);
+      const uint32_t g0 = static_cast<uint32_t>(tile_base + warp_base + lane);
+      uint32_t q = g0 / hots;
+      uint32_t r = g0 - q * hots;
+      const uint32_t step_q = 32u / hots;
+      const uint32_t step_r = 32u - step_q * hots;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int local = warp_base + i * 32 + lane;
-      val[i] = local < tile_n ? vin[tile_base + local] : KeyT(0);
+      for (int i = 0; i < ITEMS; ++i) {
+        val[i] = static_cast<KeyT>(q);
+        q += step_q;
+        r += step_r;
+        if (r >= hots) {
+          r -= hots;
+          ++q;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int local = warp_base + i * 32 + lane;
+        val[i] = local < tile_n ? vin[tile_base + local] : KeyT(0);
+      }
     }
 
     // ---- stable ranking inside the warp.  Items are warp-striped so that
@@ -689,11 +714,44 @@ void LaunchSortTyped(const SortArgs& a, uint32_t* hist, int* plan, int wbytes,
 
 }  // namespace
 
+int LaunchTransposeImpl(const void* rows, int synth_hots, const void* cols,
+                        const void* weights, int weight_dtype, int nnz,
+                        int idx_type, void* transpose_rows, void* transpose_cols,
+                        void* transpose_weights, char* work, size_t* lwork,
+                        cudaStream_t stream);
+
 int LaunchTranspose(const void* rows, const void* cols, const void* weights,
                     int weight_dtype, int nnz, int idx_type,
                     void* transpose_rows, void* transpose_cols,
                     void* transpose_weights, char* work, size_t* lwork,
                     cudaStream_t stream) {
+  return LaunchTransposeImpl(rows, 0, cols, weights, weight_dtype, nnz, idx_type,
+                             transpose_rows, transpose_cols, transpose_weights,
+                             work, lwork, stream);
+}
+
+// Fixed-hotness COO in one call: the sample id of position i is i / num_hots, so
+// the row-id array (ExtractRowIdsFromFixed) is neither written nor read; the
+// first sort pass synthesises it.
+int LaunchTransposeFixed(const void* cols, int batch_size, int num_hots,
+                         const void* weights, int weight_dtype, int idx_type,
+                         void* transpose_rows, void* transpose_cols,
+                         void* transpose_weights, char* work, size_t* lwork,
+                         cudaStream_t stream) {
+  if (batch_size < 0 || num_hots <= 0) return CUEMBED_ERR_ARGUMENT;
+  const int64_t nnz = static_cast<int64_t>(batch_size) * num_hots;
+  if (nnz >= (1 << 30)) return CUEMBED_ERR_NNZ_LIMIT;
+  return LaunchTransposeImpl(nullptr, num_hots, cols, weights, weight_dtype,
+                             static_cast<int>(nnz), idx_type, transpose_rows,
+                             transpose_cols, transpose_weights, work, lwork,
+                             stream);
+}
+
+int LaunchTransposeImpl(const void* rows, int synth_hots, const void* cols,
+                        const void* weights, int weight_dtype, int nnz,
+                        int idx_type, void* transpose_rows, void* transpose_cols,
+                        void* transpose_weights, char* work, size_t* lwork,
+                        cudaStream_t stream) {
   if (lwork == nullptr || nnz < 0) return CUEMBED_ERR_ARGUMENT;
   if (idx_type < 0 || idx_type > 1) return CUEMBED_ERR_DTYPE;
   if (weights != nullptr && (weight_dtype < 0 || weight_dtype > 2))
@@ -709,8 +767,8 @@ int LaunchTranspose(const void* rows, const void* cols, const void* weights,
   }
   if (*lwork < L.total) return CUEMBED_ERR_WORKSPACE;
   if (nnz == 0) return CUEMBED_OK;
-  if (rows == nullptr || cols == nullptr || transpose_rows == nullptr ||
-      transpose_cols == nullptr)
+  if ((rows == nullptr && synth_hots <= 0) || cols == nullptr ||
+      transpose_rows == nullptr || transpose_cols == nullptr)
     return CUEMBED_ERR_ARGUMENT;
   if (weights != nullptr && transpose_weights == nullptr)
     return CUEMBED_ERR_ARGUMENT;
@@ -740,6 +798,7 @@ int LaunchTranspose(const void* rows, const void* cols, const void* weights,
   a.num_tiles = L.num_tiles;
   a.tile_pitch = L.tile_pitch;
   a.pass = 0;
+  a.synth_hots = synth_hots;
   if (idx_type == CUEMBED_I64)
     LaunchSortTyped<int64_t>(a, hist, plan, wbytes, L.items, stream);
   else

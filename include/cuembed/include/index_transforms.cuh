@@ -84,6 +84,30 @@ void TransposeWeighted(const IndexT* rows, const IndexT* cols,
                              stream);
 }
 
+// Extension (not in the reference): ExtractRowIdsFromFixed + Transpose in one
+// call for fixed-hotness indices; the row-id array is never materialised.
+template <typename IndexT, typename WeightT>
+void TransposeFromFixed(const IndexT* cols, const WeightT* weights,
+                        const int batch_size, const int num_hots,
+                        IndexT* transpose_rows, IndexT* transpose_cols,
+                        WeightT* transpose_weights, char* work, size_t* lwork,
+                        const cudaStream_t stream = 0) {
+  if (work == nullptr) {  // workspace query: same size as Transpose
+    Transpose<IndexT, WeightT>(nullptr, cols, weights, batch_size * num_hots,
+                               transpose_rows, transpose_cols, transpose_weights,
+                               nullptr, lwork, stream);
+    return;
+  }
+  b200_detail::CheckCode(
+      cuembed_transpose_fixed(cols, batch_size, num_hots, weights,
+                              b200_detail::DTypeCode<WeightT>::value,
+                              b200_detail::ITypeCode<IndexT>::value,
+                              transpose_rows, transpose_cols, transpose_weights,
+                              work, lwork,
+                              reinterpret_cast<cuembed_stream_t>(stream)),
+      "TransposeFromFixed");
+}
+
 // [4,4,7,8,8,8,18] -> [0,0,1,2,2,2,3]
 template <typename IndexT>
 void ComputeCompressedGradIndices(const IndexT* indices, const int nnz,

@@ -160,6 +160,19 @@ int cuembed_transpose(const void* rows, const void* cols, const void* weights,
                       void* transpose_weights, char* work, size_t* lwork,
                       cuembed_stream_t stream);
 
+/*
+ * Fixed-hotness COO transposed in ONE call (new): equivalent to
+ * cuembed_extract_row_ids_fixed + cuembed_transpose, but the sample id of
+ * position i (= i / num_hots) is synthesised inside the first sort pass, so the
+ * row-id array is neither written nor read.  Same outputs, same workspace size
+ * as cuembed_transpose with nnz = batch_size * num_hots.
+ */
+int cuembed_transpose_fixed(const void* cols, int batch_size, int num_hots,
+                            const void* weights, int weight_dtype, int idx_type,
+                            void* transpose_rows, void* transpose_cols,
+                            void* transpose_weights, char* work, size_t* lwork,
+                            cuembed_stream_t stream);
+
 /* Dense rank of each element of a grouped index array:
  * [4,4,7,8,8,8,18] -> [0,0,1,2,2,2,3].  Two-call workspace protocol. */
 int cuembed_compressed_grad_indices(const void* indices, int idx_type, int nnz,

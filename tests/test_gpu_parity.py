@@ -303,6 +303,30 @@ def test_transpose_general_keys(cuda_lib, oracle, it):
         assert np.array_equal(tw.cpu().numpy(), want[2]), (nnz, lo, hi)
 
 
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("batch,hot,weighted", [(1000, 7, False), (3000, 64, True), (70000, 40, False),
+                                                (257, 1, True), (33, 100, False)])
+def test_transpose_fixed_equals_row_ids_plus_transpose(cuda_lib, oracle, it, batch, hot, weighted):
+    """cuembed_transpose_fixed synthesises the sample ids (position / hotness) in
+    the first sort pass: outputs identical to ExtractRowIdsFromFixed + Transpose
+    (and to the oracle), for hotness below, at and above the warp width and
+    tile sizes that do not divide the hotness."""
+    p = Problem(batch, 8, hot, "sum", weighted=weighted, dt=F32, index_dtype=it,
+                num_categories=5000, alpha=1.15, seed=87)
+    _, c_idx, c_sid, c_w, _ = p.cpu_transpose(oracle)
+    idx, w = gh.to_dev(p.indices), gh.to_dev(p.weights)
+    t_idx, t_sid = torch.full_like(idx, -1), torch.full_like(idx, -1)
+    t_w = torch.zeros_like(w) if w is not None else None
+    work = torch.empty(ce.Transpose(idx, idx, w, p.nnz, None, None, None, None),
+                       dtype=torch.uint8, device=gh.DEV)
+    ce.TransposeFixed(idx, w, batch, hot, t_idx, t_sid, t_w, work)
+    torch.cuda.synchronize()
+    assert np.array_equal(t_idx.cpu().numpy(), c_idx)
+    assert np.array_equal(t_sid.cpu().numpy(), c_sid)
+    if weighted:
+        assert bits_equal(gh.to_host(t_w), c_w)
+
+
 @pytest.mark.parametrize("dt", [F32, F16])
 def test_backward_long_runs_and_power_law(cuda_lib, oracle, dt):
     """Runs that span many chunks and CTAs (one row hit by every sample), and
