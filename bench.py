@@ -45,6 +45,11 @@ WORKLOADS = {
     # scaling: the global problem is fixed; N > 1 only)
     "C5": dict(num_categories=400_000_000, embed_width=128, batch_size=262144,
                hotness=64, alpha=1.15, dtype="f16", index="int32", global_problem=True),
+    # large-batch shape: same nnz as C2, but grad_y (524 288 bags = 268 MB) does
+    # not fit in L2 (the shape of one rank's local backward in the 8-way
+    # row-sharded C2)
+    "bigbatch": dict(num_categories=10_000_000, embed_width=256, batch_size=524288,
+                     hotness=8, alpha=1.15, dtype="f16", index="int32"),
     # small shape for smoke runs
     "tiny": dict(num_categories=100_000, embed_width=256, batch_size=4096,
                  hotness=64, alpha=1.15, dtype="f16", index="int32"),

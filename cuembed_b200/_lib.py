@@ -72,6 +72,7 @@ SIGNATURES = {
     "cuembed_shard_allgather_push": (_ci, [_vp, _sz, ctypes.POINTER(_vp), _ci, _ci, _vp]),
     "cuembed_microbench_gather": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_microbench_gather_bulk": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
+    "cuembed_microbench_gather_async": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }
 

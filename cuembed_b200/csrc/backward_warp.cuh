@@ -57,6 +57,10 @@ __device__ __forceinline__ typename VecBits<V>::type ZeroPlus(
   return out;
 }
 
+// Optimisation barrier on one register value (no instruction is emitted).
+__device__ __forceinline__ void PinReg(int32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void PinReg(int64_t& v) { asm volatile("" : "+l"(v)); }
+
 template <typename IdxT>
 __device__ __forceinline__ IdxT ShflDownIdx(IdxT v, int delta) {
   if constexpr (sizeof(IdxT) == 8)
@@ -162,18 +166,26 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
 #pragma unroll
   for (int e = 0; e < NE; ++e) acc[e] = 0.f;
 
-  // (key, sample, weight) of a round are requested one round ahead.
-  IdxT key_n = 0, sid_n = 0;
+  // (key, sample, weight) of a round are requested one round ahead; lane 31
+  // also requests the first key of the round after (its "next key").  Nothing
+  // may touch the words of round r + 1 before round r is over: ncu's source
+  // page showed 19 % of all warp samples on a shuffle of the just-requested
+  // key_n (the next key of lane 31) and on a register move of sid_n that the
+  // compiler had sunk into the batch loop -- one full memory latency per round
+  // with no row load in flight.
+  IdxT key_n = 0, sid_n = 0, kx_n = 0;
   T w_n = T();
   auto request = [&](int r) {
     key_n = 0;
     sid_n = 0;
+    kx_n = 0;
     w_n = T();
     const int p = r * 32 + lane;
     if (p < n) {
       key_n = __ldg(keys + c0 + p);
       sid_n = __ldg(sids + c0 + p);
       if constexpr (WEIGHTED) w_n = __ldg(weights + c0 + p);
+      if (lane == 31 && p + 1 < n) kx_n = __ldg(keys + c0 + p + 1);
     }
   };
   request(0);
@@ -203,14 +215,18 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
   for (int r = 0; r * 32 < n; ++r) {
     const int cnt = min(32, n - r * 32);
     const int p = r * 32 + lane;
-    const IdxT key = key_n, sid = sid_n;
+    IdxT key = key_n, sid = sid_n, kx = kx_n;
     const T w = w_n;
+    // the hand-over happens HERE (the words were requested a round ago), not
+    // wherever the compiler would sink it to
+    PinReg(key);
+    PinReg(sid);
+    PinReg(kx);
     request(r + 1);
     // run ends of this round: the next key is one lane to the right, the first
     // key of the next round for lane 31, `last_is_end` for the chunk's last
     IdxT knext = ShflDownIdx<IdxT>(key, 1);
-    const IdxT kfirst = ShflIdx<IdxT>(key_n, 0, 32);
-    if (lane == 31) knext = kfirst;
+    if (lane == 31) knext = kx;
     const bool end = p < n && (p == n - 1 ? last_is_end : knext != key);
     const unsigned endsw = __ballot_sync(kFull, end);
     // inverse_mapping: the lane that owns a run end writes it (load issued now,

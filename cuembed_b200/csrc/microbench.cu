@@ -187,6 +187,96 @@ int LaunchGatherBulk(const char* buf, const int* rows, long long n,
   return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
 }
 
+
+// ---- the same gather with the rows landing in shared memory through per-lane
+// 16-byte asynchronous copies (cp.async.cg, SASS LDGSTS.E.BYPASS.128): one warp
+// instruction moves one 512-byte row, like LDG.128, but the destination is the
+// lane's own shared-memory slot, so rows in flight are bounded by shared memory
+// (D batches x 8 rows x 512 B per warp) instead of registers, and a lane only
+// ever reads back what it copied itself (cp.async.wait_group, no barrier).
+template <int D, int W>
+__global__ void __launch_bounds__(W * 32)
+    GatherRowsAsyncKernel(const char* __restrict__ buf,
+                          const int* __restrict__ rows, long long n,
+                          unsigned* __restrict__ sink) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kBatch = 8;
+  extern __shared__ __align__(128) unsigned char mb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t slot0 = MbSmemAddr(mb_smem) +
+                         static_cast<uint32_t>(warp) * D * kBatch * 512 + lane * 16;
+  const long long gw = static_cast<long long>(blockIdx.x) * W + warp;
+  const long long nw = static_cast<long long>(gridDim.x) * W;
+  const char* __restrict__ base = buf + lane * 16;
+  uint32_t acc = 0;
+  // a warp takes 32 consecutive index entries per round = 4 batches of 8 rows
+  auto issue = [&](int my, int j, int slot) {
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int r = __shfl_sync(kFull, my, j * kBatch + u);
+      const char* p = base + static_cast<uint64_t>(static_cast<uint32_t>(r)) * 512;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       slot0 + (slot * kBatch + u) * 512),
+                   "l"(p)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int slot_i = 0, slot_c = 0, pending = 0;
+  auto consume = [&]() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(slot0 + (slot_c * kBatch + u) * 512)
+                   : "memory");
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    slot_c = slot_c + 1 == D ? 0 : slot_c + 1;
+  };
+  for (long long i0 = gw * 32; i0 < n; i0 += nw * 32) {
+    int my = 0;
+    if (i0 + lane < n) my = __ldg(rows + i0 + lane);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (pending == D) {
+        consume();
+        --pending;
+      }
+      issue(my, j, slot_i);
+      slot_i = slot_i + 1 == D ? 0 : slot_i + 1;
+      ++pending;
+    }
+  }
+  // drain: empty groups keep the wait count uniform
+  while (pending > 0) {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    consume();
+    --pending;
+  }
+  if (acc == 0x9e3779b9u) sink[0] = acc;
+}
+
+template <int D, int W>
+int LaunchGatherAsync(const char* buf, const int* rows, long long n, int ctas_per_sm,
+                      unsigned* sink, cudaStream_t stream) {
+  auto k = GatherRowsAsyncKernel<D, W>;
+  const size_t smem = static_cast<size_t>(W) * D * 8 * 512;
+  static PerDeviceInt configured;
+  if (configured.Get() == 0) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return CUEMBED_ERR_CUDA;
+    configured.Set(1);
+  }
+  k<<<GetDeviceInfo().sm_count * ctas_per_sm, W * 32, smem, stream>>>(buf, rows, n, sink);
+  CountLaunch();
+  return cudaPeekAtLastError() == cudaSuccess ? CUEMBED_OK : CUEMBED_ERR_CUDA;
+}
+
 }  // namespace cuembed_b200
 
 using namespace cuembed_b200;  // NOLINT
@@ -209,6 +299,29 @@ extern "C" int cuembed_microbench_gather_bulk(const void* buf, int row_bytes,
     case 2: return LaunchGatherBulk<32, 1, 12>(b, rows, n, sink, stream);
     case 3: return LaunchGatherBulk<16, 2, 12>(b, rows, n, sink, stream);
     case 4: return LaunchGatherBulk<8, 4, 12>(b, rows, n, sink, stream);
+    default: return CUEMBED_ERR_ARGUMENT;
+  }
+}
+
+// variant: 0 = 2 batches x 4 warps x 6 CTAs / SM (192 KB in flight), 1 = 3 x 4 x 4
+// (192 KB), 2 = 2 x 4 x 4 (128 KB), 3 = 4 x 4 x 3 (192 KB), 4 = 2 x 8 x 3 (192 KB)
+// (batches of 8 rows in flight per warp x warps per CTA x CTAs per SM)
+extern "C" int cuembed_microbench_gather_async(const void* buf, int row_bytes,
+                                               const int* rows, long long n,
+                                               int variant, unsigned* sink,
+                                               cuembed_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (buf == nullptr || rows == nullptr || sink == nullptr || n < 0)
+    return CUEMBED_ERR_ARGUMENT;
+  if (row_bytes != 512) return CUEMBED_ERR_ROW_BYTES;
+  if ((reinterpret_cast<uintptr_t>(buf) & 15) != 0) return CUEMBED_ERR_ARGUMENT;
+  const char* b = static_cast<const char*>(buf);
+  switch (variant) {
+    case 0: return LaunchGatherAsync<2, 4>(b, rows, n, 6, sink, stream);
+    case 1: return LaunchGatherAsync<3, 4>(b, rows, n, 4, sink, stream);
+    case 2: return LaunchGatherAsync<2, 4>(b, rows, n, 4, sink, stream);
+    case 3: return LaunchGatherAsync<4, 4>(b, rows, n, 3, sink, stream);
+    case 4: return LaunchGatherAsync<2, 8>(b, rows, n, 3, sink, stream);
     default: return CUEMBED_ERR_ARGUMENT;
   }
 }

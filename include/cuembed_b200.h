@@ -407,6 +407,14 @@ int cuembed_microbench_gather(const void* buf, int row_bytes, const int* rows,
 int cuembed_microbench_gather_bulk(const void* buf, int row_bytes,
                                    const int* rows, long long n, int variant,
                                    unsigned* sink, cuembed_stream_t stream);
+/* The same gather with per-lane 16-byte asynchronous copies (cp.async.cg, SASS
+ * LDGSTS) into the lane's own shared-memory slot, waited for with
+ * cp.async.wait_group (no barrier); row_bytes must be 512.  variant selects
+ * batches of 8 rows in flight per warp x warps per CTA x CTAs per SM:
+ * 0 = 2x4x6, 1 = 3x4x4, 2 = 2x4x4, 3 = 4x4x3, 4 = 2x8x3. */
+int cuembed_microbench_gather_async(const void* buf, int row_bytes,
+                                    const int* rows, long long n, int variant,
+                                    unsigned* sink, cuembed_stream_t stream);
 
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */

@@ -59,5 +59,9 @@ for name, (buf, idx, fl) in streams.items():
                      (3, "bulk_16x2x12"), (4, "bulk_8x4x12")):
         res[label] = run(lambda: lib.cuembed_microbench_gather_bulk(
             buf.data_ptr(), 512, idx.data_ptr(), nnz, v, sink.data_ptr(), stream.cuda_stream), fl)
+    for v, label in ((0, "async_2x4x6"), (1, "async_3x4x4"), (2, "async_2x4x4"),
+                     (3, "async_4x4x3"), (4, "async_2x8x3")):
+        res[label] = run(lambda: lib.cuembed_microbench_gather_async(
+            buf.data_ptr(), 512, idx.data_ptr(), nnz, v, sink.data_ptr(), stream.cuda_stream), fl)
     out[name] = res
 print(json.dumps(out))
