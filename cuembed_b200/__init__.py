@@ -13,12 +13,12 @@ from .api import (OPT_ADAGRAD, OPT_SGD, CombineMode, ComputeCompressedGradIndice
                   ExtractRowIdsFromCSR, ExtractRowIdsFromFixed, ShardFinalize,
                   ShardSelect, Transpose, backward_workspace_bytes, launch_count,
                   EmbeddingForwardHot, HotRowsFromSorted, forward_hot_capacity,
-                  TransposeFixed)
+                  TransposeFixed, EmbeddingForwardMapped, DebugCheckLookup)
 
 __all__ = [
     "CombineMode", "CuEmbedError", "EmbeddingForward", "EmbeddingBackward", "EmbeddingBackwardUpdate", "EmbeddingForwardMulti", "OPT_SGD", "OPT_ADAGRAD",
     "ExtractRowIdsFromFixed", "ExtractRowIdsFromCSR", "ExtractRowIdsForConcat",
     "Transpose", "ComputeCompressedGradIndices", "backward_workspace_bytes",
     "launch_count", "ShardSelect", "ShardFinalize", "EmbeddingForwardHot", "HotRowsFromSorted",
-    "forward_hot_capacity", "TransposeFixed",
+    "forward_hot_capacity", "TransposeFixed", "EmbeddingForwardMapped", "DebugCheckLookup",
 ]

@@ -21,6 +21,8 @@ SIGNATURES = {
     "cuembed_error_string": (ctypes.c_char_p, [_ci]),
     "cuembed_forward": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci,
                               _ci, _ci, _vp, _ci, _vp]),
+    "cuembed_forward_mapped": (_ci, [_vp, _ci, _ci, _vp, _ci, _vp, _ci, _vp, _ci, _ci,
+                                     _ci, _vp, _ci, _vp, _vp, _vp]),
     "cuembed_forward_multi": (_ci, [_ci, ctypes.POINTER(_vp), _ci, _ci,
                                     ctypes.POINTER(_vp), _ci, ctypes.POINTER(_vp), _ci,
                                     ctypes.POINTER(_vp), ctypes.POINTER(_ci),
@@ -72,6 +74,8 @@ SIGNATURES = {
     "cuembed_shard_allgather_push": (_ci, [_vp, _sz, ctypes.POINTER(_vp), _ci, _ci, _vp]),
     "cuembed_microbench_gather": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_microbench_gather_bulk": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
+    "cuembed_debug_check_lookup": (_ci, [_vp, _ci, ctypes.c_longlong, ctypes.c_longlong, _vp, _ci, _ci,
+                                         ctypes.POINTER(ctypes.c_longlong), _vp]),
     "cuembed_microbench_gather_async": (_ci, [_vp, _ci, _vp, ctypes.c_longlong, _ci, _vp, _vp]),
     "cuembed_launch_count": (ctypes.c_ulonglong, []),
 }

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import enum
+import os
 from typing import Optional
 
 import torch
@@ -29,6 +30,9 @@ class CombineMode(enum.IntEnum):
 class CuEmbedError(RuntimeError):
     pass
 
+
+# CUEMBED_DEBUG_CHECKS=1: EmbeddingForward validates its indices / offsets first
+_DEBUG_CHECKS = os.environ.get("CUEMBED_DEBUG_CHECKS", "0") not in ("", "0")
 
 _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _IT = {torch.int32: 0, torch.int64: 1}
@@ -90,12 +94,73 @@ def EmbeddingForward(params: torch.Tensor, embed_width: int,
     if weights is not None and weights.dtype != params.dtype:
         raise CuEmbedError("weights must have the element type of params "
                            "(GetElemT<InputT>, embedding_lookup.cuh:249)")
+    if _DEBUG_CHECKS:
+        DebugCheckLookup(indices, params.shape[0], offsets,
+                         batch_size if offsets is not None else None,
+                         nnz=None if offsets is not None else batch_size * num_hots,
+                         stream=stream)
     _check(lib.cuembed_forward(
         _dev(params, "params"), _dt(params), int(embed_width),
         _dev(indices, "indices"), _it(indices),
         _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
         _dev(weights, "weights"), int(batch_size), int(num_hots), int(mode),
         int(bool(fp16_math)), _dev(ret, "ret"), _dt(ret), _stream(stream)))
+
+
+def DebugCheckLookup(indices: torch.Tensor, num_rows: int,
+                     offsets: Optional[torch.Tensor] = None,
+                     batch_size: Optional[int] = None, nnz: Optional[int] = None,
+                     stream=None) -> None:
+    """cuembed_debug_check_lookup: validates a lookup's indices (all in
+    [0, num_rows)) and CSR offsets (non-negative, ascending, within nnz) on the
+    device; raises CuEmbedError naming the first offending position.  The
+    kernels themselves carry no bounds checks, like the reference's
+    (cuembed/include/embedding_lookup_ops.cuh:59).  Synchronises the stream.
+    Setting CUEMBED_DEBUG_CHECKS=1 makes EmbeddingForward call it on every
+    lookup."""
+    lib = _lib.load()
+    n = int(indices.numel() if nnz is None else nnz)
+    if offsets is not None and batch_size is None:
+        batch_size = offsets.numel() - 1
+    first = ctypes.c_longlong(-1)
+    rc = lib.cuembed_debug_check_lookup(
+        _dev(indices, "indices"), _it(indices), n, int(num_rows),
+        _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+        int(batch_size or 0), ctypes.byref(first), _stream(stream))
+    if rc != 0:
+        what = "bag" if rc == -11 else "lookup"
+        raise CuEmbedError(f"cuembed_b200 error {rc}: {lib.cuembed_error_string(rc).decode()} "
+                           f"(first offending {what}: {first.value})")
+
+
+def EmbeddingForwardMapped(params: torch.Tensor, embed_width: int,
+                           indices: torch.Tensor, offsets: Optional[torch.Tensor],
+                           weights: Optional[torch.Tensor], batch_size: int,
+                           num_hots: int, mode: CombineMode, ret: torch.Tensor,
+                           row_map: torch.Tensor,
+                           cache_params: Optional[torch.Tensor] = None,
+                           stream=None) -> None:
+    """cuembed_forward_mapped: EmbeddingForward through an addresser indirection
+    (the reference's embedding-cache hook, embedding_lookup_kernels.cuh:114-115):
+    row_map[i] >= 0 reads row row_map[i] of `cache_params` (of `params` when no
+    cache table is given), row_map[i] < 0 reads row i of `params`.  `params` only
+    has to be device-accessible (e.g. a pinned host tensor mapped into the
+    device's address space is the caller's business; here a CUDA tensor)."""
+    lib = _lib.load()
+    if weights is not None and weights.dtype != params.dtype:
+        raise CuEmbedError("weights must have the element type of params")
+    if row_map.dtype != indices.dtype:
+        raise CuEmbedError("row_map must have the integer type of indices")
+    if cache_params is not None and (cache_params.dtype != params.dtype or
+                                     cache_params.shape[1] != params.shape[1]):
+        raise CuEmbedError("cache_params must have the dtype and row width of params")
+    _check(lib.cuembed_forward_mapped(
+        _dev(params, "params"), _dt(params), int(embed_width),
+        _dev(indices, "indices"), _it(indices),
+        _dev(offsets, "offsets"), _it(offsets) if offsets is not None else 0,
+        _dev(weights, "weights"), int(batch_size), int(num_hots), int(mode),
+        _dev(ret, "ret"), _dt(ret), _dev(row_map, "row_map"),
+        _dev(cache_params, "cache_params"), _stream(stream)))
 
 
 def forward_hot_capacity(dtype: torch.dtype, embed_width: int) -> int:

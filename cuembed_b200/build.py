@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcuembed_b200.so")
 SOURCES = ["c_api.cu", "forward.cu", "transforms.cu", "backward.cu", "sharded.cu",
-           "sharded_p2p.cu", "microbench.cu", "forward_hot.cu"]
+           "sharded_p2p.cu", "microbench.cu", "forward_hot.cu", "debug.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", LIB_PATH, *objs]
+               "-o", LIB_PATH, *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -3,10 +3,26 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "launch.h"
 
 namespace cuembed_b200 {
+
+// CUEMBED_NVTX=1: every entry point opens an NVTX range around its launches
+// (the header-only NVTX v3 costs one branch when no tool listens).
+struct NvtxScope {
+  bool on;
+  explicit NvtxScope(const char* name) {
+    static const int enabled = EnvInt("CUEMBED_NVTX", 0);
+    on = enabled != 0;
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxScope() {
+    if (on) nvtxRangePop();
+  }
+};
 
 static std::atomic<unsigned long long> g_launches{0};
 
@@ -51,6 +67,10 @@ const char* cuembed_error_string(int code) {
       return "a CUDA runtime call or kernel launch failed";
     case CUEMBED_ERR_NNZ_LIMIT:
       return "nnz must be < 2^30 for transpose";
+    case CUEMBED_ERR_INDEX_RANGE:
+      return "debug check: a lookup index lies outside [0, num_rows)";
+    case CUEMBED_ERR_OFFSETS:
+      return "debug check: offsets are negative, not ascending or exceed nnz";
     default:
       return "unknown error";
   }
@@ -61,10 +81,27 @@ int cuembed_forward(const void* params, int in_dtype, int embed_width,
                     int off_type, const void* weights, int batch_size,
                     int num_hots, int mode, int fp16_math, void* ret,
                     int out_dtype, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_forward");
   return LaunchForward(params, in_dtype, embed_width, indices, idx_type,
                        offsets, off_type, weights, batch_size, num_hots, mode,
                        fp16_math, ret, out_dtype,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_forward_mapped(const void* params, int in_dtype, int embed_width,
+                           const void* indices, int idx_type,
+                           const void* offsets, int off_type,
+                           const void* weights, int batch_size, int num_hots,
+                           int mode, void* ret, int out_dtype,
+                           const void* row_map, const void* cache_params,
+                           cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_forward_mapped");
+  if (row_map == nullptr) return CUEMBED_ERR_ARGUMENT;
+  return LaunchForward(params, in_dtype, embed_width, indices, idx_type,
+                       offsets, off_type, weights, batch_size, num_hots, mode,
+                       /*fp16_math=*/0, ret, out_dtype,
+                       reinterpret_cast<cudaStream_t>(stream), row_map,
+                       cache_params);
 }
 
 int cuembed_forward_multi(int num_tables, const void* const* params,
@@ -75,6 +112,7 @@ int cuembed_forward_multi(int num_tables, const void* const* params,
                           const int* num_hots, const int* modes,
                           void* const* rets, int out_dtype,
                           long long out_row_stride, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_forward_multi");
   return LaunchForwardMulti(num_tables, params, in_dtype, embed_width, indices,
                             idx_type, offsets, off_type, weights, batch_sizes,
                             num_hots, modes, rets, out_dtype, out_row_stride,
@@ -83,6 +121,7 @@ int cuembed_forward_multi(int num_tables, const void* const* params,
 
 int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
                                   int idx_type, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_extract_row_ids_fixed");
   return LaunchExtractRowIdsFixed(batch_size, num_hots, row_ids, idx_type,
                                   reinterpret_cast<cudaStream_t>(stream));
 }
@@ -90,6 +129,7 @@ int cuembed_extract_row_ids_fixed(int batch_size, int num_hots, void* row_ids,
 int cuembed_extract_row_ids_csr(const void* offsets, int off_type,
                                 int batch_size, void* row_ids, int idx_type,
                                 cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_extract_row_ids_csr");
   return LaunchExtractRowIdsCsr(offsets, off_type, batch_size, row_ids,
                                 idx_type,
                                 reinterpret_cast<cudaStream_t>(stream));
@@ -97,6 +137,7 @@ int cuembed_extract_row_ids_csr(const void* offsets, int off_type,
 
 int cuembed_extract_row_ids_concat(int nnz, void* row_ids, int idx_type,
                                    cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_extract_row_ids_concat");
   return LaunchExtractRowIdsConcat(nnz, row_ids, idx_type,
                                    reinterpret_cast<cudaStream_t>(stream));
 }
@@ -106,6 +147,7 @@ int cuembed_transpose(const void* rows, const void* cols, const void* weights,
                       void* transpose_rows, void* transpose_cols,
                       void* transpose_weights, char* work, size_t* lwork,
                       cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_transpose");
   return LaunchTranspose(rows, cols, weights, weight_dtype, nnz, idx_type,
                          transpose_rows, transpose_cols, transpose_weights,
                          work, lwork, reinterpret_cast<cudaStream_t>(stream));
@@ -116,6 +158,7 @@ int cuembed_transpose_fixed(const void* cols, int batch_size, int num_hots,
                             void* transpose_rows, void* transpose_cols,
                             void* transpose_weights, char* work, size_t* lwork,
                             cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_transpose_fixed");
   return LaunchTransposeFixed(cols, batch_size, num_hots, weights, weight_dtype,
                               idx_type, transpose_rows, transpose_cols,
                               transpose_weights, work, lwork,
@@ -125,6 +168,7 @@ int cuembed_transpose_fixed(const void* cols, int batch_size, int num_hots,
 int cuembed_compressed_grad_indices(const void* indices, int idx_type, int nnz,
                                     void* remapped_indices, char* work,
                                     size_t* lwork, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_compressed_grad_indices");
   return LaunchCompressedGradIndices(indices, idx_type, nnz, remapped_indices,
                                      work, lwork,
                                      reinterpret_cast<cudaStream_t>(stream));
@@ -138,6 +182,7 @@ int cuembed_backward_ws(const void* grad_y, int dtype, int embed_width,
                         const void* transpose_weights, int skip_grad_init,
                         void* grad_embedding, void* inverse_mapping,
                         char* work, size_t* lwork, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_backward_ws");
   return LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows,
                         nnz, idx_type, transpose_indices, transpose_sample_ids,
                         transpose_remapped_indices, transpose_weights,
@@ -152,6 +197,7 @@ int cuembed_backward_update(const void* grad_y, int dtype, int embed_width,
                             const void* transpose_weights, int optimizer,
                             float lr, float eps, void* params, float* state,
                             char* work, size_t* lwork, cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_backward_update");
   return LaunchBackwardUpdate(grad_y, dtype, embed_width, nnz, idx_type,
                               transpose_indices, transpose_sample_ids,
                               transpose_weights, optimizer, lr, eps, params,
@@ -171,6 +217,7 @@ int cuembed_backward(const void* grad_y, int dtype, int embed_width,
                      const void* transpose_weights, int skip_grad_init,
                      void* grad_embedding, void* inverse_mapping,
                      cuembed_stream_t stream_) {
+  NvtxScope nvtx_scope("cuembed_backward");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   size_t lwork = 0;
   int rc = LaunchBackward(grad_y, dtype, embed_width, num_grad_embedding_rows,
@@ -258,6 +305,17 @@ int cuembed_shard_finalize(const void* partial_f32, int n_samples,
                              off_type, num_hots, sample0, weights, weight_dtype,
                              out, out_dtype,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cuembed_debug_check_lookup(const void* indices, int idx_type, long long nnz,
+                               long long num_rows, const void* offsets,
+                               int off_type, int batch_size,
+                               long long* first_bad_position,
+                               cuembed_stream_t stream) {
+  NvtxScope nvtx_scope("cuembed_debug_check_lookup");
+  return LaunchDebugCheckLookup(indices, idx_type, nnz, num_rows, offsets,
+                                off_type, batch_size, first_bad_position,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 unsigned long long cuembed_launch_count(void) { return g_launches.load(); }

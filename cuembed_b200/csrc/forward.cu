@@ -50,28 +50,28 @@ int PersistentGrid(const void* kernel, PerDeviceInt* occ_cache,
   return static_cast<int>(g < 1 ? 1 : g);
 }
 
+// UNROLL = 8 row loads in flight per lane group (4 and 16 were measured slower
+// in round 1 and are no longer built).
 template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP>
 void LaunchPool(const FwdArgs& a, cudaStream_t stream) {
-  static const int unroll = EnvInt("CUEMBED_FWD_UNROLL", 8);
   const int groups_per_cta = kCtaThreads / a.lanes;
   const int64_t work_ctas = (a.batch + groups_per_cta - 1) / groups_per_cta;
-  static PerDeviceInt occ4, occ8, occ16;
-  if (unroll == 4) {
-    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 4>;
-    const int grid =
-        PersistentGrid(reinterpret_cast<const void*>(k), &occ4, work_ctas);
-    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
-  } else if (unroll == 16 && V == 16) {
-    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, (V == 16 ? 16 : 8)>;
-    const int grid =
-        PersistentGrid(reinterpret_cast<const void*>(k), &occ16, work_ctas);
-    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
-  } else {
-    auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 8>;
-    const int grid =
-        PersistentGrid(reinterpret_cast<const void*>(k), &occ8, work_ctas);
-    k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
+  if constexpr (!LOWP) {
+    if (a.row_map != nullptr) {
+      static PerDeviceInt occ_mapped;
+      auto k = FwdPoolMappedKernel<T, V, IdxT, WEIGHTED>;
+      const int grid = PersistentGrid(reinterpret_cast<const void*>(k),
+                                      &occ_mapped, work_ctas);
+      k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
+      CountLaunch();
+      return;
+    }
   }
+  static PerDeviceInt occ8;
+  auto k = FwdPoolKernel<T, V, IdxT, WEIGHTED, LOWP, 8>;
+  const int grid =
+      PersistentGrid(reinterpret_cast<const void*>(k), &occ8, work_ctas);
+  k<<<dim3(grid, a.col_tiles), kCtaThreads, 0, stream>>>(a);
   CountLaunch();
 }
 
@@ -259,6 +259,8 @@ int LaunchForwardMulti(int num_tables, const void* const* params, int in_dtype,
     for (int t = t0; t < num_tables && t < t0 + kMaxTablesPerLaunch; ++t) {
       if (batch_sizes[t] == 0) continue;
       FwdArgs& a = m.t[n++];
+      a.row_map = nullptr;
+      a.cache = nullptr;
       a.params = params[t];
       a.indices = indices[t];
       a.offsets = offsets != nullptr ? offsets[t] : nullptr;
@@ -301,7 +303,13 @@ int LaunchForward(const void* params, int in_dtype, int embed_width,
                   const void* indices, int idx_type, const void* offsets,
                   int off_type, const void* weights, int batch_size,
                   int num_hots, int mode, int fp16_math, void* ret,
-                  int out_dtype, cudaStream_t stream) {
+                  int out_dtype, cudaStream_t stream, const void* row_map,
+                  const void* cache_params) {
+  // the addresser indirection exists for the pooled modes with fp32 accumulation
+  if (row_map == nullptr && cache_params != nullptr) return CUEMBED_ERR_ARGUMENT;
+  if (row_map != nullptr &&
+      (mode == CUEMBED_CONCAT || (fp16_math != 0 && in_dtype != CUEMBED_F32)))
+    return CUEMBED_ERR_ARGUMENT;
   // Same argument checks as the reference host function,
   // cuembed/include/embedding_lookup.cuh:260-267.
   if (weights != nullptr && mode == CUEMBED_CONCAT)
@@ -370,12 +378,15 @@ int LaunchForward(const void* params, int in_dtype, int embed_width,
   // matching output store is an argument error, not a misaligned access.
   const int v = PickPoolVector(
       shape.vec_bytes,
-      reinterpret_cast<uint64_t>(params) | static_cast<uint64_t>(row_bytes),
+      reinterpret_cast<uint64_t>(params) | reinterpret_cast<uint64_t>(cache_params) |
+          static_cast<uint64_t>(row_bytes),
       reinterpret_cast<uint64_t>(ret) | static_cast<uint64_t>(out_row_bytes),
       in_dtype, out_dtype);
   if (v == 0) return CUEMBED_ERR_ARGUMENT;
 
   FwdArgs a;
+  a.row_map = row_map;
+  a.cache = cache_params;
   a.params = params;
   a.indices = indices;
   a.offsets = offsets;

@@ -24,6 +24,13 @@ struct FwdArgs {
   int lanes;
   int log2_lanes;
   int col_tiles;
+  // Addresser indirection (the "embedding cache" hook the reference leaves as a
+  // comment, cuembed/include/embedding_lookup_kernels.cuh:114-115 and
+  // embedding_lookup_ops.cuh:62-63): row_map[i] >= 0 sends lookup i to row
+  // row_map[i] of `cache` (of `params` when cache is null); row_map[i] < 0 keeps
+  // row i of `params`.  Null = the identity (MAPPED kernels only).
+  const void* row_map;
+  const void* cache;
 };
 
 template <typename T, int V, bool LOWP>
@@ -166,7 +173,7 @@ __device__ __forceinline__ uint64_t RowOffset(IdxT row, uint32_t row_bytes) {
 #endif
 
 template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP,
-          int UNROLL>
+          int UNROLL, bool MAPPED = false>
 __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
   using VecT = typename VecBits<V>::type;
   using AccT = Accum<T, V, LOWP>;
@@ -186,6 +193,26 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
   // table base + this lane's column offset in one (opaque) register pair, so a
   // row address is a single IMAD.WIDE (common.cuh RowAddr)
   asm volatile("" : "+l"(params));
+  // MAPPED: lookups are translated when their index round is requested; a
+  // translated word t >= 0 is row t of the cache table, t < 0 is row ~t of the
+  // backing table (so one register still carries a lookup through the shuffles).
+  const IdxT* __restrict__ row_map = static_cast<const IdxT*>(a.row_map);
+  const char* cache = params;
+  if constexpr (MAPPED) {
+    if (a.cache != nullptr) {
+      cache = static_cast<const char*>(a.cache) +
+              static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+      asm volatile("" : "+l"(cache));
+    }
+  }
+  auto translate = [&](IdxT raw) -> IdxT {
+    if constexpr (MAPPED) {
+      const IdxT slot = __ldg(row_map + raw);
+      return slot >= 0 ? slot : static_cast<IdxT>(~raw);
+    } else {
+      return raw;
+    }
+  };
   const IdxT* __restrict__ indices = static_cast<const IdxT*>(a.indices);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
   uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
@@ -230,6 +257,14 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
       idx_nxt = __ldg(bag_idx + G + lane_g);
       if constexpr (WEIGHTED) w_nxt = __ldg(bag_w + G + lane_g);
     }
+    // MAPPED: one more round of raw indices in flight, so that a translation is
+    // only ever requested for an index that arrived a round ago
+    IdxT raw_nn = 0;
+    if constexpr (MAPPED) {
+      if (2 * G + lane_g < len) raw_nn = __ldg(bag_idx + 2 * G + lane_g);
+      idx_cur = translate(idx_cur);
+      idx_nxt = translate(idx_nxt);
+    }
 #pragma unroll 1
     for (int j0 = 0; j0 < len_max; j0 += G) {
       const int cnt = min(G, len - j0);  // may be <= 0 for a finished group
@@ -249,7 +284,14 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
         for (int u = 0; u < UNROLL; ++u) {
           const IdxT row = ShflIndex<IdxT>(kFull, idx_rot, u, G);
           if constexpr (WEIGHTED) wv[u] = ShflElem<T>(kFull, w_rot, u, G);
-          vals[u] = LdgVec<V>(RowAddr<IdxT>(params, row, row_bytes));
+          if constexpr (MAPPED) {
+            const bool direct = row < 0;
+            vals[u] = LdgVec<V>(RowAddr<IdxT>(direct ? params : cache,
+                                              direct ? static_cast<IdxT>(~row) : row,
+                                              row_bytes));
+          } else {
+            vals[u] = LdgVec<V>(RowAddr<IdxT>(params, row, row_bytes));
+          }
         }
         idx_rot = ShflIndex<IdxT>(kFull, idx_rot, rot_from, G);
         if constexpr (WEIGHTED) w_rot = ShflElem<T>(kFull, w_rot, rot_from, G);
@@ -280,7 +322,14 @@ __device__ __forceinline__ void FwdPoolBody(const FwdArgs& a) {
       idx_cur = idx_nxt;
       idx_nxt = 0;
       if constexpr (WEIGHTED) w_cur = w_nxt;
-      if (j0 + 2 * G + lane_g < len) {
+      if constexpr (MAPPED) {
+        idx_nxt = translate(raw_nn);  // requested a round ago
+        raw_nn = 0;
+        if (j0 + 3 * G + lane_g < len) raw_nn = __ldg(bag_idx + j0 + 3 * G + lane_g);
+        if constexpr (WEIGHTED) {
+          if (j0 + 2 * G + lane_g < len) w_nxt = __ldg(bag_w + j0 + 2 * G + lane_g);
+        }
+      } else if (j0 + 2 * G + lane_g < len) {
         idx_nxt = __ldg(bag_idx + j0 + 2 * G + lane_g);
         if constexpr (WEIGHTED) w_nxt = __ldg(bag_w + j0 + 2 * G + lane_g);
       }
@@ -308,6 +357,13 @@ template <typename T, int V, typename IdxT, bool WEIGHTED, bool LOWP,
 __global__ void __launch_bounds__(kCtaThreads, FWD_MINB(UNROLL))
     FwdPoolKernel(const FwdArgs a) {
   FwdPoolBody<T, V, IdxT, WEIGHTED, LOWP, UNROLL>(a);
+}
+
+// The pooled kernel with the addresser indirection (FwdArgs::row_map / cache).
+template <typename T, int V, typename IdxT, bool WEIGHTED>
+__global__ void __launch_bounds__(kCtaThreads, FWD_MINB(8))
+    FwdPoolMappedKernel(const FwdArgs a) {
+  FwdPoolBody<T, V, IdxT, WEIGHTED, false, 8, true>(a);
 }
 
 // Multi-table batched lookup (the reference is "single

@@ -17,7 +17,14 @@ int LaunchForward(const void* params, int in_dtype, int embed_width,
                   const void* indices, int idx_type, const void* offsets,
                   int off_type, const void* weights, int batch_size,
                   int num_hots, int mode, int fp16_math, void* ret,
-                  int out_dtype, cudaStream_t stream);
+                  int out_dtype, cudaStream_t stream,
+                  const void* row_map = nullptr,
+                  const void* cache_params = nullptr);
+
+int LaunchDebugCheckLookup(const void* indices, int idx_type, long long nnz,
+                           long long num_rows, const void* offsets, int off_type,
+                           int batch_size, long long* first_bad_position,
+                           cudaStream_t stream);
 
 int LaunchForwardMulti(int num_tables, const void* const* params, int in_dtype,
                        int embed_width, const void* const* indices,

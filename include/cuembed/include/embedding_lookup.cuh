@@ -55,6 +55,21 @@ void EmbeddingForward(const InputT* params, const int embed_width,
                       const int num_hots, const CombineMode mode, OutputT* ret,
                       const cudaStream_t stream = 0) {
   using ElemT = GetElemT<InputT>;
+  if constexpr (b200_detail::IsMappedTable<InputT>::value) {
+    // structured InputT: `params` is a host pointer to one MappedTable
+    CUEMBED_ASSERT(params != nullptr && params->row_map != nullptr);
+    CUEMBED_ASSERT(!fp16_math && mode != CombineMode::kConcat);
+    b200_detail::CheckCode(
+        cuembed_forward_mapped(
+            params->rows, b200_detail::DTypeCode<ElemT>::value, embed_width,
+            indices, b200_detail::ITypeCode<IndexT>::value, offsets,
+            b200_detail::ITypeCode<OffsetT>::value, weights, batch_size,
+            num_hots, b200_detail::ModeCode(mode), ret,
+            b200_detail::DTypeCode<GetElemT<OutputT>>::value, params->row_map,
+            params->cache, reinterpret_cast<cuembed_stream_t>(stream)),
+        "EmbeddingForward<MappedTable>");
+    return;
+  } else {
   b200_detail::CheckCode(
       cuembed_forward(params, b200_detail::DTypeCode<ElemT>::value, embed_width,
                       indices, b200_detail::ITypeCode<IndexT>::value, offsets,
@@ -64,6 +79,26 @@ void EmbeddingForward(const InputT* params, const int embed_width,
                       b200_detail::DTypeCode<GetElemT<OutputT>>::value,
                       reinterpret_cast<cuembed_stream_t>(stream)),
       "EmbeddingForward");
+  }
+}
+
+// Debug aid (new): validates indices / offsets on the device and aborts with
+// the first offending position; synchronises the stream.  The kernels carry
+// no bounds checks, like the reference's (embedding_lookup_ops.cuh:59).
+template <typename IndexT, typename OffsetT>
+void DebugCheckLookup(const IndexT* indices, const long long nnz,
+                      const long long num_rows, const OffsetT* offsets,
+                      const int batch_size, const cudaStream_t stream = 0) {
+  long long first = -1;
+  const int code = cuembed_debug_check_lookup(
+      indices, b200_detail::ITypeCode<IndexT>::value, nnz, num_rows, offsets,
+      b200_detail::ITypeCode<OffsetT>::value, batch_size, &first,
+      reinterpret_cast<cuembed_stream_t>(stream));
+  if (code != CUEMBED_OK) {
+    std::cerr << "DebugCheckLookup: " << cuembed_error_string(code)
+              << " (first offending position " << first << ")" << std::endl;
+    std::abort();
+  }
 }
 
 // Gradient w.r.t. the table from the transposed COO indices; full or

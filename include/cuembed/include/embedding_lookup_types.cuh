@@ -74,6 +74,35 @@ struct GetElemType {
 template <typename T>
 using GetElemT = typename GetElemType<T>::Type;
 
+// A structured InputT (new): a table seen through an addresser indirection --
+// what the reference's comments reserve for an embedding cache ("float with
+// cache", :576-578; "templatize the addresser with the cache",
+// embedding_lookup_kernels.cuh:114-115).  Lookup i reads row row_map[i] of
+// `cache` (of `rows` itself when cache is null) if row_map[i] >= 0, else row i
+// of `rows`.  EmbeddingForward<MappedTable<ElemT, IndexT>, ...> takes a HOST
+// pointer to one such descriptor as `params`; weights stay `const ElemT*`
+// through the GetElemType specialisation below.  Sum / mean, fp32 accumulation.
+template <typename ElemT, typename IndexT>
+struct MappedTable {
+  const ElemT* rows;        // backing table [num_rows, width], device-accessible
+  const IndexT* row_map;    // [num_rows], device
+  const ElemT* cache;       // cache table [slots, width] or nullptr, device
+};
+template <typename ElemT, typename IndexT>
+struct GetElemType<MappedTable<ElemT, IndexT>> {
+  using Type = ElemT;
+};
+namespace b200_detail {
+template <typename T>
+struct IsMappedTable {
+  static constexpr bool value = false;
+};
+template <typename ElemT, typename IndexT>
+struct IsMappedTable<MappedTable<ElemT, IndexT>> {
+  static constexpr bool value = true;
+};
+}  // namespace b200_detail
+
 // Element / index type -> C ABI code (include/cuembed_b200.h).
 namespace b200_detail {
 template <typename T>

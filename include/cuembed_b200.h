@@ -69,6 +69,8 @@ typedef struct CUstream_st* cuembed_stream_t;
 #define CUEMBED_ERR_ARGUMENT (-7)        /* null / negative argument */
 #define CUEMBED_ERR_CUDA (-8)            /* a CUDA runtime call failed */
 #define CUEMBED_ERR_NNZ_LIMIT (-9)       /* nnz >= 2^30 in transpose */
+#define CUEMBED_ERR_INDEX_RANGE (-10)    /* debug check: an index outside [0, rows) */
+#define CUEMBED_ERR_OFFSETS (-11)        /* debug check: offsets not ascending / out of range */
 
 /* Library / ABI version and the SM architecture the kernels were built for. */
 int cuembed_version(void);
@@ -90,6 +92,30 @@ int cuembed_forward(const void* params, int in_dtype, int embed_width,
                     int off_type, const void* weights, int batch_size,
                     int num_hots, int mode, int fp16_math, void* ret,
                     int out_dtype, cuembed_stream_t stream);
+
+/*
+ * Pooled lookup through an addresser indirection (new): the hook the reference
+ * reserves for an embedding cache ("sample_id directly corresponds to the
+ * physical row ... this may change with an index mapping or an embedding
+ * cache", cuembed/include/embedding_lookup_ops.cuh:62-63; "templatize the
+ * addresser with the cache", embedding_lookup_kernels.cuh:114-115).
+ * row_map [rows of params] of idx_type:
+ *   row_map[i] >= 0 : lookup i reads row row_map[i] of cache_params
+ *                     (of params itself when cache_params is NULL: a pure
+ *                     index remapping);
+ *   row_map[i] <  0 : lookup i reads row i of params (not cached); params may
+ *                     be any device-accessible memory, e.g. pinned host memory.
+ * cache_params has the dtype and row width of params.  Sum / mean only, fp32
+ * accumulation; everything else as cuembed_forward, and the result is
+ * bit-identical to cuembed_forward on the table the mapping describes.
+ */
+int cuembed_forward_mapped(const void* params, int in_dtype, int embed_width,
+                           const void* indices, int idx_type,
+                           const void* offsets, int off_type,
+                           const void* weights, int batch_size, int num_hots,
+                           int mode, void* ret, int out_dtype,
+                           const void* row_map, const void* cache_params,
+                           cuembed_stream_t stream);
 
 /*
  * Multi-table batched lookup (new; the reference is "single table",
@@ -415,6 +441,24 @@ int cuembed_microbench_gather_bulk(const void* buf, int row_bytes,
 int cuembed_microbench_gather_async(const void* buf, int row_bytes,
                                     const int* rows, long long n, int variant,
                                     unsigned* sink, cuembed_stream_t stream);
+
+/*
+ * Debug aid (new).  The reference removes every bounds check from its kernels
+ * (cuembed/include/embedding_lookup_ops.cuh:59) and so does this library; this
+ * call validates a lookup's inputs on the device instead: every index must lie
+ * in [0, num_rows), and (offsets != NULL) the offsets must be non-negative,
+ * non-decreasing and end at or below nnz.  It SYNCHRONISES the stream.  Returns
+ * CUEMBED_OK, CUEMBED_ERR_OFFSETS or CUEMBED_ERR_INDEX_RANGE, with the first
+ * offending position (bag for offsets, lookup for indices) in
+ * *first_bad_position (-1 if none; may be NULL).
+ * With CUEMBED_NVTX=1 in the environment every entry point of this library
+ * also opens an NVTX range named after itself around its launches.
+ */
+int cuembed_debug_check_lookup(const void* indices, int idx_type, long long nnz,
+                               long long num_rows, const void* offsets,
+                               int off_type, int batch_size,
+                               long long* first_bad_position,
+                               cuembed_stream_t stream);
 
 /* Number of kernels this library has launched in this process (all threads);
  * used by bench.py to report `gpu_launches`. */

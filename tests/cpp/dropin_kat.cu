@@ -175,6 +175,35 @@ int RunAll(const char* tag) {
   CUDA_OK(cudaDeviceSynchronize());
   failures += !Equal(ret2, {18, 20, 22, 24, 9, 10, 11, 12, 18, 20, 22, 24, 9, 10, 11, 12},
                      "multi-table forward");
+  // ---- structured InputT: a table behind an addresser indirection
+  // (cuembed::MappedTable, the reference's embedding-cache hook).  Row 1 is
+  // served from slot 0 of a cache table, row 4 is remapped to ... itself
+  // uncached; rows 0 and 3 stay in the backing table.
+  {
+    std::vector<float> cache_v = {101, 102, 103, 104};
+    ElemT* cache = Managed<ElemT>(cache_v);
+    IndexT* row_map = ManagedI<IndexT>({-1, 0, -1, -1, -1});
+    cuembed::MappedTable<ElemT, IndexT> mapped = {params, row_map, cache};
+    ElemT* ret3 = Managed<ElemT>(std::vector<float>(8, -1.f));
+    cuembed::EmbeddingForward<cuembed::MappedTable<ElemT, IndexT>, ElemT, IndexT, int>(
+        &mapped, 4, indices, no_offsets, no_weights, 2, 2, CombineMode::kSum, ret3);
+    CUDA_OK(cudaDeviceSynchronize());
+    // bag 0 = rows {1 -> cache slot 0, 3}, bag 1 = rows {0, 4}
+    failures += !Equal(ret3, {101 + 13, 102 + 14, 103 + 15, 104 + 16, 18, 20, 22, 24},
+                       "mapped table forward");
+    // pure remapping inside the table: row 3 reads row 0
+    IndexT* row_map2 = ManagedI<IndexT>({-1, -1, -1, 0, -1});
+    cuembed::MappedTable<ElemT, IndexT> remap = {params, row_map2, nullptr};
+    cuembed::EmbeddingForward<cuembed::MappedTable<ElemT, IndexT>, ElemT, IndexT, int>(
+        &remap, 4, indices, offsets, weights, 2, 0, CombineMode::kSum, ret3);
+    CUDA_OK(cudaDeviceSynchronize());
+    // bag 0 = 1 * row 1 + 0.5 * row 0, bag 1 = 1 * row 0 + 0.5 * row 4
+    failures += !Equal(ret3, {5.5f, 7, 8.5f, 10, 9.5f, 11, 12.5f, 14}, "remapped forward");
+  }
+  // ---- debug bounds check: the valid lookup passes (an invalid one aborts,
+  // which the Python tests exercise through the C ABI)
+  cuembed::DebugCheckLookup<IndexT, int>(indices, 4, 5, offsets, 2);
+
   std::printf("%s: %s\n", tag, failures == 0 ? "PASS" : "FAIL");
   return failures;
 }

@@ -9,7 +9,8 @@ import cuembed_b200 as ce
 import gpu_helpers as gh
 import helpers
 from golden import kat
-from helpers import Problem, bits_equal, cast_elems, to_f32, value_equal
+from cuembed_b200 import datagen
+from helpers import Problem, bits_equal, cast_elems, raw, to_f32, value_equal
 from oracle.cpu_lib import BF16, CONCAT, F16, F32, MEAN, SUM, Bf16
 
 pytestmark = pytest.mark.gpu
@@ -672,3 +673,81 @@ def test_backward_real_valued_tolerance(cuda_lib, oracle):
         # deterministic: a second run is bit-identical
         g2, _, _ = gh.gpu_backward(p, t_idx, t_sid, t_w, remapped)
         assert bits_equal(g_grad, g2)
+
+
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("mode,csr,weighted,width,hot,with_cache", [
+    ("sum", False, False, 256, 64, True),    # the headline row shape, 2 index rounds per bag
+    ("sum", False, True, 64, 100, True),     # 4 rounds per bag: the translation pipeline
+    ("mean", True, False, 128, 40, True),    # ragged bags
+    ("sum", True, True, 24, 7, False),       # pure remapping inside one table, 4-byte vectors
+    ("sum", False, False, 1024, 3, False),   # column tiles
+])
+def test_forward_mapped_addresser(cuda_lib, oracle, dt, it, mode, csr, weighted, width, hot,
+                                  with_cache):
+    """cuembed_forward_mapped (the reference's embedding-cache addresser hook,
+    cuembed/include/embedding_lookup_kernels.cuh:114-115): about a third of the
+    rows are redirected to scattered slots of a second (cache) table -- or to
+    other rows of the same table -- and the rest read the backing table.  The
+    output must be bit-identical to the oracle's forward on the table that the
+    mapping describes."""
+    p = Problem(777, width, hot, mode, csr=csr, weighted=weighted, dt=dt, index_dtype=it,
+                num_categories=5000, alpha=1.05, seed=55)
+    rng = np.random.default_rng(5)
+    n = p.num_categories
+    cached = rng.random(n) < 0.35
+    row_map = np.full(n, -1, dtype=it)
+    table_bits = raw(p.table)
+    if with_cache:
+        n_slots = int(cached.sum()) + 17
+        slots = rng.permutation(n_slots)[:int(cached.sum())]
+        row_map[cached] = slots.astype(it)
+        cache_f32 = datagen.make_table(n_slots, width, seed=99)
+        cache = cast_elems(cache_f32, dt)
+        effective = table_bits.copy()
+        effective[cached] = raw(cache)[slots]
+    else:
+        targets = rng.integers(0, n, size=int(cached.sum()))
+        row_map[cached] = targets.astype(it)
+        cache = None
+        effective = table_bits.copy()
+        effective[cached] = table_bits[targets]
+    saved = p.table
+    p.table = Bf16(effective) if isinstance(saved, Bf16) else effective
+    want = p.cpu_forward(oracle)
+    p.table = saved
+    ret = torch.full((p.batch, width), float("nan"), dtype=gh.TORCH_DT[dt], device=gh.DEV)
+    ce.EmbeddingForwardMapped(gh.to_dev(p.table), width, gh.to_dev(p.indices),
+                              gh.to_dev(p.offsets), gh.to_dev(p.weights), p.batch,
+                              p.num_hots, ce.CombineMode(p.mode), ret,
+                              gh.to_dev(row_map), gh.to_dev(cache))
+    torch.cuda.synchronize()
+    assert bits_equal(gh.to_host(ret), want)
+    # concat and fp16_math have no mapped form: an argument error, not a wrong result
+    with pytest.raises(ce.CuEmbedError):
+        ce.EmbeddingForwardMapped(gh.to_dev(p.table), width, gh.to_dev(p.indices), None, None,
+                                  4, 2, ce.CombineMode.kConcat,
+                                  torch.empty(8, width, dtype=gh.TORCH_DT[dt], device=gh.DEV),
+                                  gh.to_dev(row_map), None)
+
+
+@pytest.mark.parametrize("it", ITS)
+def test_debug_check_lookup(cuda_lib, it):
+    """cuembed_debug_check_lookup: the optional bounds check next to kernels that
+    (like the reference's, embedding_lookup_ops.cuh:59) carry none."""
+    p = Problem(300, 8, 12, "sum", csr=True, index_dtype=it, num_categories=1000, seed=3)
+    idx, off = gh.to_dev(p.indices), gh.to_dev(p.offsets)
+    ce.DebugCheckLookup(idx, 1000, off)                      # valid: no error
+    ce.DebugCheckLookup(idx, 1000)                           # fixed hotness form
+    bad = idx.clone()
+    bad[37] = 1000                                           # one past the end
+    bad[200] = -5
+    with pytest.raises(ce.CuEmbedError, match=r"outside \[0, num_rows\).*lookup: 37"):
+        ce.DebugCheckLookup(bad, 1000, off)
+    bad_off = off.clone()
+    bad_off[11] = bad_off[12] + 1                            # bag 11 ends before it starts
+    with pytest.raises(ce.CuEmbedError, match=r"offsets.*bag: 10|offsets.*bag: 11"):
+        ce.DebugCheckLookup(idx, 1000, bad_off)
+    with pytest.raises(ce.CuEmbedError, match="offsets"):
+        ce.DebugCheckLookup(idx[:-3], 1000, off)             # offsets run past nnz
