@@ -340,7 +340,7 @@ def run_p2p(args, rank, local_rank, world):
                        ("sort_with_grad_push" if emb.select_first else
                         "select_sort_with_grad_push"): {"ms": round(tr_ms, 4)},
                        "backward": {"ms": round(bwd_ms, 4)}},
-            "roofline": {"bound": "hbm", "kernel": "ShardPoolPushKernel + BwdSegReduceKernel (local)",
+            "roofline": {"bound": "hbm", "kernel": "ShardPoolPushKernel + BwdWarpKernel (local)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None,
                          "peak_source": peak_src,
@@ -558,7 +558,7 @@ def run_nccl(args, rank, local_rank, world, transport_note=None):
             "stages": {"forward": {"ms": round(fwd_ms, 4)}, "transpose": {"ms": round(tr_ms, 4)},
                        "backward": {"ms": round(bwd_ms, 4)},
                        "collectives_alone_ms": {k: round(v, 4) for k, v in comm.items()}},
-            "roofline": {"bound": "hbm", "kernel": "BwdSegReduceKernel (local) + collectives",
+            "roofline": {"bound": "hbm", "kernel": "BwdWarpKernel (local) + collectives",
                          "achieved": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, 1),
                          "peak": peak, "unit": "GB/s",
                          "frac": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak, 4),
