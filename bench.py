@@ -492,6 +492,10 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its version banner on STDOUT, in front
+        # of the one JSON line this program owes its caller: keep warnings only
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         from benchmarks import sharded_bench
         return sharded_bench.run(args, rank, local_rank, world)

@@ -330,8 +330,11 @@ def run_p2p(args, rank, local_rank, world):
                        "select_first": bool(emb.select_first),
                        "sizes": ("local nnz / num_unique known from an earlier identical step "
                                  "(--known-sizes): no host read-back" if known_sizes else
-                                 "local nnz and num_unique read back by the host in every step "
-                                 "(2 stream syncs per step, inside the timed region)"),
+                                 "local nnz and num_unique read back by the host in every step, "
+                                 "inside the timed region: local nnz is summed from the pool "
+                                 "kernel's counts and copied on the side stream under the exchange; "
+                                 "num_unique is read after the backward has been launched into "
+                                 "upper-bound buffers"),
                        "nnz_global": nnz, "nnz_local_rank0": local_nnz,
                        "num_unique_rank0": num_unique,
                        "nvlink_bytes_out_per_rank": {"forward": nvlink_fwd, "backward": nvlink_bwd},

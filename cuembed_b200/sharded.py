@@ -149,12 +149,21 @@ class CudaLocalOps:
         t_idx, t_sid, t_w, remapped = coo
         dev = grad_y.device
         width = grad_y.shape[1]
+        if grad is None and remapped is not None:
+            # Compressed gradient of unknown size: launch into buffers sized for the
+            # upper bound (every owned lookup a distinct row) and read the number of
+            # unique rows back AFTER the launch, so the read-back waits under the
+            # backward instead of leaving the GPU idle in front of it.  The result
+            # is a view of the first `rows` rows.
+            cap = max(1, min(local_nnz, num_local_rows))
+            grad = torch.empty(cap, width, dtype=grad_y.dtype, device=dev)
+            inv = torch.empty(cap, dtype=t_idx.dtype, device=dev)
+            api.EmbeddingBackward(grad_y, width, cap, local_nnz, t_idx, t_sid, remapped,
+                                  t_w, True, grad, inv)
+            rows = int(remapped[-1].item()) + 1
+            return grad[:rows], inv[:rows]
         if grad is None:
-            rows = num_local_rows
-            if remapped is not None:
-                rows = int(remapped[-1].item()) + 1  # the caller sizes the gradient
-                inv = torch.empty(rows, dtype=t_idx.dtype, device=dev)
-            grad = torch.empty(rows, width, dtype=grad_y.dtype, device=dev)
+            grad = torch.empty(num_local_rows, width, dtype=grad_y.dtype, device=dev)
         rows = grad.shape[0]
         # every row of a compressed gradient is written: no zero-fill needed
         api.EmbeddingBackward(grad_y, width, rows, local_nnz, t_idx, t_sid, remapped,

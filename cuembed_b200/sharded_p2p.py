@@ -46,6 +46,10 @@ class PeerForwardContext:
     coo: Optional[tuple] = None
     local_nnz: int = -1
     selected: Optional[tuple] = None   # (local_offsets, local_indices, sample_ids, local_weights)
+    # the number of owned lookups, summed from the pool kernel's per-bag counts and
+    # copied to the host on the side stream while the exchange runs
+    nnz_host: Optional[torch.Tensor] = None
+    nnz_event: Optional[torch.cuda.Event] = None
 
 
 class PeerShardedEmbedding:
@@ -108,6 +112,7 @@ class PeerShardedEmbedding:
         # the data path never synchronises with the host)
         self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._status_event = None
+        self._nnz_host = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
 
     # ------------------------------------------------------------ plumbing
     def _buffer(self, kind: str, nbytes: int):
@@ -236,8 +241,23 @@ class PeerShardedEmbedding:
         ctx = PeerForwardContext(indices, offsets, weights, counts, batch_size,
                                  num_hots, mode)
         ctx.selected = selected
-        if selected is not None and local_nnz is not None:
+        if local_nnz is not None:
             ctx.local_nnz = int(local_nnz)
+        elif selected is None and (stream is None or isinstance(stream, torch.cuda.Stream)):
+            # The backward's sort is sized by the number of lookups this rank owns.
+            # The pool kernel has just counted them per bag: sum the counts and copy
+            # the total to the host on the side stream, under the exchange, so that
+            # prepare_backward finds it there instead of stalling the main stream
+            # on a read-back after the select.
+            main = stream if stream is not None else torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                host = self._nnz_host[epoch & 1]
+                host.copy_(counts.sum(dtype=torch.int64).view(1), non_blocking=True)
+                ctx.nnz_host = host
+                ctx.nnz_event = torch.cuda.Event()
+                ctx.nnz_event.record(self._side)
+            counts.record_stream(self._side)
         return ("pool", ctx, buf, base, epoch, out_dtype, stream)
 
     def forward_finish(self, pending):
@@ -316,6 +336,11 @@ class PeerShardedEmbedding:
                 raise CuEmbedError("sharded concat backward needs nnz < 2^31")
             weights = torch.arange(ctx.indices.numel(), dtype=torch.int32,
                                    device=self.device).view(torch.float32)
+        if local_nnz is None and ctx.local_nnz >= 0:
+            local_nnz = ctx.local_nnz
+        if local_nnz is None and ctx.nnz_event is not None and not concat:
+            ctx.nnz_event.synchronize()        # recorded under the forward's exchange
+            local_nnz = int(ctx.nnz_host.item())
         if ctx.selected is not None and not concat:
             l_off, l_idx, l_sid, l_w = ctx.selected   # selected before the forward
         else:
