@@ -704,12 +704,14 @@ BwdLayout MakeBwdLayout(int nnz, int embed_width, int lanes, int dtype) {
 template <typename T, int V, typename IdxT, bool WEIGHTED>
 void LaunchSegReduce(const BwdArgs& a, int col_tiles, cudaStream_t stream) {
   dim3 grid(a.num_ctas, col_tiles);
+  // the warp walker: one chunk per warp, BWD_WARP_CTA_WARPS chunks per CTA
+  const dim3 wgrid(a.num_chunks / BWD_WARP_CTA_WARPS, col_tiles);
   if (a.warp_path && a.opt_kind == CUEMBED_OPT_SGD)
     BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_SGD>
-        <<<grid, kBwdThreads, 0, stream>>>(a);
+        <<<wgrid, kBwdWarpThreads, 0, stream>>>(a);
   else if (a.warp_path && a.opt_kind == CUEMBED_OPT_NONE)
     BwdWarpKernel<T, V, IdxT, WEIGHTED, CUEMBED_OPT_NONE>
-        <<<grid, kBwdThreads, 0, stream>>>(a);
+        <<<wgrid, kBwdWarpThreads, 0, stream>>>(a);
   else if (a.opt_kind == CUEMBED_OPT_ADAGRAD)
     BwdSegReduceKernel<T, V, IdxT, WEIGHTED, 4, CUEMBED_OPT_ADAGRAD>
         <<<grid, kBwdThreads, 0, stream>>>(a);  // 4: room for the old rows

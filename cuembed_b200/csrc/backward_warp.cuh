@@ -31,11 +31,29 @@
 namespace cuembed_b200 {
 
 #ifndef BWD_WARP_MINB
-#define BWD_WARP_MINB 6
+#define BWD_WARP_MINB 7
 #endif
 #ifndef BWD_WARP_UNROLL
 #define BWD_WARP_UNROLL 8
 #endif
+// Warps (= chunks) per CTA of the warp walker: ONE.  A CTA holds its slot on the
+// SM until its slowest warp is done, and chunks differ in cost (interiors of hot
+// runs take the branch-free path, cold chunks end a run at every nonzero); with
+// four chunks per CTA ncu showed 30.6 % achieved occupancy against 37.5 %
+// theoretical.  (The SM holds at most 32 CTAs, i.e. 32 such warps.)
+#ifndef BWD_WARP_CTA_WARPS
+#define BWD_WARP_CTA_WARPS 1
+#endif
+constexpr int kBwdWarpThreads = 32 * BWD_WARP_CTA_WARPS;
+// Resident warps per SM the register allocation aims at: 4 * BWD_WARP_MINB (28
+// -> at most 72 registers) for the lean instantiations (32-bit indices,
+// unweighted, plain gradient), 4 fewer for the others, which would spill at 72.
+// Measured at C2 (profiles/r02_notes.md): one-warp CTAs at 28 warps per SM
+// 0.1938 ms, at 24 warps 0.2024, four-warp CTAs at 24 warps 0.2109; 32 warps
+// (64 registers, spills) 0.2005.
+constexpr int BwdWarpMinBlocks(bool lean) {
+  return (lean ? BWD_WARP_MINB : BWD_WARP_MINB - 1) * 4 / BWD_WARP_CTA_WARPS;
+}
 // round_T(0.f + float(x)) for every 16-bit element of a vector: x itself except
 // that -0 becomes +0 (what a sum that starts at +0 gives).
 template <typename T, int V>
@@ -97,7 +115,9 @@ __device__ __forceinline__ T ShflRaw(T w, int src) {
 // FUSED_OPT: CUEMBED_OPT_NONE or CUEMBED_OPT_SGD (Adagrad stays on the generic
 // kernel: it needs the old table rows in flight).
 template <typename T, int V, typename IdxT, bool WEIGHTED, int FUSED_OPT>
-__global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
+__global__ void __launch_bounds__(
+    kBwdWarpThreads,
+    BwdWarpMinBlocks(sizeof(IdxT) == 4 && !WEIGHTED && FUSED_OPT == CUEMBED_OPT_NONE))
     BwdWarpKernel(const BwdArgs a) {
   using VecT = typename VecBits<V>::type;
   constexpr int NW = V / 4;
@@ -108,7 +128,7 @@ __global__ void __launch_bounds__(kBwdThreads, BWD_WARP_MINB)
       !WEIGHTED && FUSED_OPT == CUEMBED_OPT_NONE && sizeof(T) == 2;
 
   const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
+  const int chunk = blockIdx.x * BWD_WARP_CTA_WARPS + (threadIdx.x >> 5);
   const IdxT* __restrict__ keys = static_cast<const IdxT*>(a.keys);
   const IdxT* __restrict__ sids = static_cast<const IdxT*>(a.sids);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
