@@ -342,7 +342,7 @@ __device__ __forceinline__ uint4 LdVolatile4(const uint32_t* p) {
 // with a smaller id, which were taken earlier, so the look-back cannot
 // deadlock.
 template <typename KeyT, int WBYTES, int ITEMS>
-__global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : 2))
+__global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : (ITEMS <= 12 ? 3 : 2)))
     RadixPassKernel(const SortArgs a) {
   constexpr int TILE = ITEMS * kCtaThreads;
   using WT = typename std::conditional<WBYTES == 4, uint32_t, uint16_t>::type;
@@ -629,12 +629,17 @@ SortLayout MakeSortLayout(int nnz, int idx_type, int wbytes) {
   SortLayout L;
   const int nd = static_cast<int>(IndexSize(idx_type));
   static const int items_env = EnvInt("CUEMBED_SORT_ITEMS", 0);
-  // 16 keys per thread (4096-key tiles) once there are enough tiles to keep the
-  // SMs busy: fewer per-tile fixed costs (counter reset, digit scan, look-back);
-  // measured at C2 under graph replay: transpose 0.177 -> 0.170 ms.  Smaller
+  // Larger tiles once there are enough of them to keep the SMs busy: fewer
+  // per-tile fixed costs (counter reset, digit scan, look-back).  Smaller
   // problems keep 2048-key tiles for parallelism.
-  L.items = items_env > 0 ? items_env : (nnz >= (2 << 20) ? 16 : 8);
-  if (L.items != 8 && L.items != 16) L.items = 8;
+  // 32-bit keys: 12 keys per thread (3072-key tiles, 80 registers, THREE CTAs =
+  // 24 warps per SM).  Measured at C2 (graph replay, same box, transpose stage):
+  // 8 keys 0.173, 10 keys 0.170, 12 keys 0.161-0.163, 14 keys 0.168, 16 keys
+  // 0.172 ms -- 16 keys need 128 registers (16 warps per SM), 8 and 10 pay the
+  // per-tile fixed costs more often.  64-bit keys would spill at 80 registers
+  // and keep 16.
+  L.items = items_env > 0 ? items_env : (nnz >= (2 << 20) ? (nd == 4 ? 12 : 16) : 8);
+  if (L.items != 8 && L.items != 12 && L.items != 16) L.items = 8;
   L.tile = L.items * kCtaThreads;
   L.num_tiles = nnz > 0 ? (nnz + L.tile - 1) / L.tile : 0;
   size_t off = 0;
@@ -689,6 +694,8 @@ template <typename KeyT, int WBYTES>
 void LaunchPassesItems(const SortArgs& a, int items, cudaStream_t stream) {
   if (items == 16)
     LaunchPasses<KeyT, WBYTES, 16>(a, stream);
+  else if (items == 12)
+    LaunchPasses<KeyT, WBYTES, 12>(a, stream);
   else
     LaunchPasses<KeyT, WBYTES, 8>(a, stream);
 }
