@@ -164,8 +164,11 @@ struct PushArgs {
 
 constexpr int kQueuePerWarp = 128;
 
+#ifndef PUSH_MINB
+#define PUSH_MINB 4
+#endif
 template <typename T, int V, typename IdxT, bool WEIGHTED>
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, PUSH_MINB)
     ShardPoolPushKernel(const PushArgs a) {
   using VecT = typename VecBits<V>::type;
   using AccT = Accum<T, V, false>;
@@ -191,13 +194,26 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
 
   const int v = blockIdx.y * G + lane_g;
   const bool active = v < a.nvec;
-  const char* __restrict__ params =
-      static_cast<const char*>(a.params) +
-      static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  // table base + this lane's column offset in one opaque register pair and a
+  // plain 32-bit pitch: a row address is a single IMAD.WIDE (common.cuh RowAddr;
+  // ncu had counted 576 warp instructions per bag at 8 ranks, 16 of them
+  // reloading the table pointer from the constant bank for every batch)
+  const char* params = static_cast<const char*>(a.params) +
+                       static_cast<int64_t>(active ? v : a.nvec - 1) * V;
+  asm volatile("" : "+l"(params));
   const IdxT* __restrict__ indices = static_cast<const IdxT*>(a.indices);
   const T* __restrict__ weights = static_cast<const T*>(a.weights);
-  const uint64_t row_bytes = static_cast<uint64_t>(a.row_bytes);
+  uint32_t row_bytes = static_cast<uint32_t>(a.row_bytes);
+  asm volatile("" : "+r"(row_bytes));
   const int warp_first = group - gw;
+  const unsigned long long span = static_cast<unsigned long long>(a.hi - a.lo);
+
+  // seq = smod + world * sdiv, advanced by total_groups per bag without a
+  // division (two runtime divisions per bag were ~40 instructions)
+  const int step_div = total_groups / a.world;
+  const int step_mod = total_groups - step_div * a.world;
+  int sdiv = (warp_first + gw) / a.world;
+  int smod = (warp_first + gw) - sdiv * a.world;
 
 #pragma unroll 1
   for (int seq0 = warp_first; seq0 < a.batch; seq0 += total_groups) {
@@ -206,9 +222,15 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
     // Consecutive bags go to consecutive owners, starting at rank + 1: the
     // NVLink pushes are spread evenly over the whole kernel (they overlap the
     // bags pooled for the rank itself) and over the receivers.
-    int owner = a.rank + 1 + seq % a.world;
+    int owner = a.rank + 1 + smod;
     if (owner >= a.world) owner -= a.world;
-    const int bag = owner * a.per + seq / a.world;
+    const int bag = owner * a.per + sdiv;
+    smod += step_mod;
+    sdiv += step_div;
+    if (smod >= a.world) {
+      smod -= a.world;
+      ++sdiv;
+    }
     int64_t start = 0;
     int len = 0;
     if (bag_ok) {
@@ -221,6 +243,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
       }
     }
     const int len_max = (G == 32) ? len : __reduce_max_sync(kFull, len);
+    const bool fits = len_max <= qcap;
     const IdxT* __restrict__ bag_idx = indices + start;
     const T* __restrict__ bag_w = weights + start;
 
@@ -246,31 +269,52 @@ __global__ void __launch_bounds__(kCtaThreads, 4)
           idx_nxt = __ldg(bag_idx + j0 + G + lane_g);
           if constexpr (WEIGHTED) w_nxt = __ldg(bag_w + j0 + G + lane_g);
         }
-        const long long row = static_cast<long long>(idx_cur);
-        const bool keep = (j0 + lane_g < len) && row >= a.lo && row < a.hi;
+        // owned <=> 0 <= row - lo < hi - lo: one unsigned compare (the shard has
+        // fewer than 2^32 rows, checked by the launcher)
+        const unsigned long long rel =
+            static_cast<unsigned long long>(static_cast<long long>(idx_cur) - a.lo);
+        const bool keep = (j0 + lane_g < len) && rel < span;
         const unsigned m = (__ballot_sync(kFull, keep) >> gshift) & gmask;
         if (keep) {
           const int slot = qn + __popc(m & lt);
-          q[slot] = static_cast<uint32_t>(row - a.lo);
+          q[slot] = static_cast<uint32_t>(rel);
           if constexpr (WEIGHTED) qw[slot] = w_cur;
         }
         qn += __popc(m);
         kept += __popc(m);
         idx_cur = idx_nxt;
         if constexpr (WEIGHTED) w_cur = w_nxt;
-        __syncwarp();
       }
-      if (!more || __any_sync(kFull, qn + G > qcap)) {
+      // a bag that fits the queue as a whole is pooled once, at its end
+      if (!more || (!fits && __any_sync(kFull, qn + G > qcap))) {
+        __syncwarp();  // the queue entries of all lanes are visible
         // Pool the queued rows in queue (= bag) order, UNROLL loads in flight.
         const int qmax = (G == 32) ? qn : __reduce_max_sync(kFull, qn);
 #pragma unroll 1
         for (int jb = 0; jb < qmax; jb += UNROLL) {
           VecT vals[UNROLL];
           T wv[UNROLL];
+          const bool whole = (G == 32) ? (jb + UNROLL <= qn)
+                                       : __all_sync(kFull, jb + UNROLL <= qn);
+          if (whole) {  // a full batch in every lane group: nothing predicated
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              vals[u] = LdgVec<V>(RowAddr<uint32_t>(params, q[jb + u], row_bytes));
+              if constexpr (WEIGHTED) wv[u] = qw[jb + u];
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              if constexpr (WEIGHTED)
+                acc.AddWeighted(vals[u], wv[u]);
+              else
+                acc.Add(vals[u]);
+            }
+            continue;
+          }
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u) {
             if (jb + u < qn) {
-              vals[u] = LdgVec<V>(params + q[jb + u] * row_bytes);
+              vals[u] = LdgVec<V>(RowAddr<uint32_t>(params, q[jb + u], row_bytes));
               if constexpr (WEIGHTED) wv[u] = qw[jb + u];
             }
           }
