@@ -42,8 +42,21 @@ for W in worlds:
         e0.record(stream); push(); e1.record(stream); torch.cuda.synchronize()
         if it: times.append(e0.elapsed_time(e1))
     kept = int(counts.sum().item())
+    # the backward's select (counts from the push kernel): scan + fill of the local COO
+    from cuembed_b200.sharded import CudaLocalOps
+    ops = CudaLocalOps()
+    sel = []
+    for it in range(6):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ops.shard_select_coo(indices, None, None, batch, hot, 0, shard_rows, counts=counts,
+                             nnz_cap=kept)
+        e1.record(stream); torch.cuda.synchronize()
+        if it: sel.append(e0.elapsed_time(e1))
     print(json.dumps({"world": W, "global_batch": batch, "lookups_scanned": batch * hot,
                       "lookups_owned": kept, "push_kernel_ms": round(min(times), 4),
-                      "median_ms": round(sorted(times)[len(times) // 2], 4)}))
+                      "median_ms": round(sorted(times)[len(times) // 2], 4),
+                      "select_coo_ms": round(min(sel), 4)}))
     group.close()
     del indices, counts
