@@ -492,10 +492,14 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its version banner on STDOUT, in front
-        # of the one JSON line this program owes its caller: keep warnings only
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # With NCCL_DEBUG set NCCL prints its version banner on STDOUT, in front of
+        # the one JSON line this program owes its caller.  File descriptor 1 is
+        # pointed at stderr for everything that is not ours; the JSON line goes to
+        # the original stdout (sys.stdout is rebound to it at the end of the run).
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = real_stdout
         dist.init_process_group("nccl", device_id=dev)
         from benchmarks import sharded_bench
         return sharded_bench.run(args, rank, local_rank, world)
