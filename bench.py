@@ -56,6 +56,13 @@ WORKLOADS = {
 }
 
 
+def workload_string(name, cfg):
+    """The same text in the line of this library and in the reference arm's."""
+    return (f"manual_benchmark default ({name}): {cfg['num_categories']}x{cfg['embed_width']} "
+            f"{cfg['dtype']}, batch {cfg['batch_size']}, hotness {cfg['hotness']}, "
+            f"alpha {cfg['alpha']}, {cfg['index']} indices, sum, compressed grad")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -852,9 +859,7 @@ def run_gpu(args):
         "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": cfg["dtype"], "data": "synthetic",
-        "config": {"workload": f"manual_benchmark default ({args.workload}): "
-                               f"{rows}x{w} {cfg['dtype']}, batch {batch}, hotness {hot}, "
-                               f"alpha {cfg['alpha']}, {cfg['index']} indices, sum, compressed grad",
+        "config": {"workload": workload_string(args.workload, cfg),
                    "l2": "flushed before every stage (512 MB write)",
                    "launch": launch_mode,
                    "transpose": ("ExtractRowIdsFromFixed + Transpose + ComputeCompressedGradIndices"
@@ -894,11 +899,12 @@ def run_reference(args):
     kind_lib, kind = cpu_kind()
     threads = host_threads()
     batch = cfg["batch_size"]
-    sample_bags = min(batch, args.cpu_sample_bags)
+    # the reference arm runs the WHOLE batch by default (about 1.5 s per step on
+    # 16 host threads at C2); --ref-sample-bags bounds it for slower hosts
+    sample_bags = batch if args.ref_sample_bags <= 0 else min(batch, args.ref_sample_bags)
     wl = make_host_inputs(cfg, batch)
     from cuembed_b200 import datagen
-    # The CPU path only touches the rows its sample references, but the table
-    # must exist at full size for the indices to be valid.
+    # The table must exist at full size for the indices to be valid.
     rng = np.random.default_rng(123456)
     dt = np.float16 if cfg["dtype"] == "f16" else np.float32
     table = np.empty((cfg["num_categories"], cfg["embed_width"]), dt)
@@ -920,8 +926,10 @@ def run_reference(args):
             stage[k] += t[k]
     ms = tot / args.steps * 1e3
     value = s_nnz / (ms * 1e-3)
-    sample = (f"first {sample_bags} of {batch} bags ({s_nnz} lookups) per step; fwd and bwd "
-              f"sliced over {threads} threads, transpose single-threaded as in the reference")
+    sample = ((f"the whole batch ({batch} bags, {s_nnz} lookups) per step" if sample_bags == batch
+               else f"first {sample_bags} of {batch} bags ({s_nnz} lookups) per step")
+              + f"; fwd and bwd sliced over {threads} threads, transpose single-threaded as in "
+                f"the reference")
     line = {
         "impl": "reference",
         "metric": "lookups/s (fwd + transpose + bwd, compressed grad)",
@@ -929,8 +937,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": cfg["dtype"], "data": "synthetic",
-        "config": {"workload": f"manual_benchmark default ({args.workload}), CPU reference path "
-                               f"({'oracle/_ref: reference templates' if kind == 'reference' else 'oracle port'})",
+        "config": {"workload": workload_string(args.workload, cfg),
+                   "arm": ("the reference's own CPU implementation of the path "
+                           + ("(oracle/_ref: its templates compiled unchanged)" if kind == "reference"
+                              else "(oracle port)") + f" on {threads} host threads"),
                    "sample": sample},
         "cpu_baseline": {"value": round(value, 1), "unit": "lookups/s", "cores": threads,
                          "kind": kind, "sample": sample,
@@ -949,6 +959,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-bags", type=int, default=8192)
+    ap.add_argument("--ref-sample-bags", type=int, default=0,
+                    help="--impl reference: bags per step (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--separate-row-ids", action="store_true",
