@@ -527,7 +527,15 @@ __global__ void __launch_bounds__(kCtaThreads, (ITEMS <= 8 ? 4 : (ITEMS <= 12 ? 
     // profiles/r01_notes.md).
     uint32_t exclusive = 0;
     if (tile > 0) {
-      constexpr int kLookWin = 8;
+// predecessors per look-back round.  With 12 keys per thread and three CTAs per
+// SM the predecessors publish early; measured at C2 (transpose stage, ms):
+// 1 -> 0.1609, 2 -> 0.1568, 3 -> 0.1592, 4 -> 0.158, 6 -> 0.1588, 8 -> 0.163,
+// 16 -> 0.1715, 32 -> 0.207 (wide windows fetch status words that are not
+// published yet and poll them again).
+#ifndef RADIX_LOOK_WIN
+#define RADIX_LOOK_WIN 2
+#endif
+      constexpr int kLookWin = RADIX_LOOK_WIN;
       int prev = tile - 1;
       bool done = false;
       while (!done) {
