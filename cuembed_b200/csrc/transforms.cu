@@ -644,9 +644,10 @@ SortLayout MakeSortLayout(int nnz, int idx_type, int wbytes) {
   // 24 warps per SM).  Measured at C2 (graph replay, same box, transpose stage):
   // 8 keys 0.173, 10 keys 0.170, 12 keys 0.161-0.163, 14 keys 0.168, 16 keys
   // 0.172 ms -- 16 keys need 128 registers (16 warps per SM), 8 and 10 pay the
-  // per-tile fixed costs more often.  64-bit keys would spill at 80 registers
-  // and keep 16.
-  L.items = items_env > 0 ? items_env : (nnz >= (2 << 20) ? (nd == 4 ? 12 : 16) : 8);
+  // per-tile fixed costs more often.  64-bit keys (they would spill at 80
+  // registers with 12): 8 keys per thread, measured on the C3 shape (int64
+  // indices, weights, 4.2 M pairs): 8 -> 0.2915, 12 -> 0.314, 16 -> 0.3085 ms.
+  L.items = items_env > 0 ? items_env : (nnz >= (2 << 20) && nd == 4 ? 12 : 8);
   if (L.items != 8 && L.items != 12 && L.items != 16) L.items = 8;
   L.tile = L.items * kCtaThreads;
   L.num_tiles = nnz > 0 ? (nnz + L.tile - 1) / L.tile : 0;
