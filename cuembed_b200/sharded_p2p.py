@@ -338,15 +338,19 @@ class PeerShardedEmbedding:
                                    device=self.device).view(torch.float32)
         if local_nnz is None and ctx.local_nnz >= 0:
             local_nnz = ctx.local_nnz
-        if local_nnz is None and ctx.nnz_event is not None and not concat:
-            ctx.nnz_event.synchronize()        # recorded under the forward's exchange
-            local_nnz = int(ctx.nnz_host.item())
+        pending_nnz = local_nnz is None and ctx.nnz_event is not None and not concat
         if ctx.selected is not None and not concat:
             l_off, l_idx, l_sid, l_w = ctx.selected   # selected before the forward
         else:
+            # With the count still on its way to the host the select is launched
+            # into buffers sized for the whole index list, so that the GPU has the
+            # select to run while the host waits for the number that sizes the sort.
             l_off, l_idx, l_sid, l_w = self.ops.shard_select_coo(
                 ctx.indices, ctx.offsets, weights, ctx.batch, ctx.num_hots, self.lo,
                 self.hi, counts=ctx.counts, nnz_cap=local_nnz)
+        if pending_nnz:
+            ctx.nnz_event.synchronize()        # recorded under the forward's exchange
+            local_nnz = int(ctx.nnz_host.item())
         if local_nnz is not None:
             ctx.local_nnz = int(local_nnz)
         elif ctx.local_nnz < 0:
